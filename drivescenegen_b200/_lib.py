@@ -1,0 +1,90 @@
+"""ctypes binding of libdsg_b200.so (the C ABI declared in include/dsg_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a ``DsgError`` is raised.  The loader only
+looks at the in-tree build product (``drivescenegen_b200/libdsg_b200.so``); build it with
+``python -m drivescenegen_b200.build`` or ``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdsg_b200.so")
+
+
+class DsgError(RuntimeError):
+    pass
+
+
+class ConvArgs(C.Structure):
+    """mirror of ``dsg_conv_args`` (include/dsg_b200.h)."""
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("x", C.c_void_p),
+        ("sc1", C.c_void_p), ("csc1", C.c_int32),
+        ("sc2", C.c_void_p), ("csc2", C.c_int32),
+        ("wpacked", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("temb", C.c_void_p),
+        ("temb_stride", C.c_int32), ("temb_off", C.c_int32),
+        ("residual", C.c_void_p),
+        ("out", C.c_void_p),
+        ("block_n", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+_i32, _i64, _p, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/dsg_b200.h declares (tests check this)
+SIGNATURES = {
+    "dsg_version": (C.c_int, []),
+    "dsg_last_error": (C.c_char_p, []),
+    "dsg_launch_count": (_i64, []),
+    "dsg_device_ok": (C.c_int, []),
+    "dsg_ddpm_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
+    "dsg_ddim_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
+    "dsg_add_noise": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _p]),
+    "dsg_latent_to_image": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dsg_time_embed": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p]),
+    "dsg_conv_in": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dsg_conv_out": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dsg_gn_chunks": (_i32, [_i64]),
+    "dsg_gn_stats": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p]),
+    "dsg_gn_apply": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _i64, _i32, _p]),
+    "dsg_conv": (C.c_int, [C.POINTER(ConvArgs), _p]),
+    "dsg_packed_k": (_i64, [_i32, _i32, _i32]),
+    "dsg_packed_rows": (_i64, [_i32, _i32]),
+    "dsg_pack_conv_weight": (C.c_int, [_i32, _p, _i32, _i32, _p, _i32, _p, _p]),
+    "dsg_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library (once) and bind every signature; raises DsgError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DsgError(f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                       "Build it with `python -m drivescenegen_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().dsg_last_error()
+        raise DsgError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().dsg_launch_count())

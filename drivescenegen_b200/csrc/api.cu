@@ -1,0 +1,37 @@
+// api.cu — error reporting, version, launch accounting.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace dsg {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace dsg
+
+extern "C" {
+int dsg_version(void) { return 100; }
+const char* dsg_last_error(void) { return dsg::g_err; }
+int64_t dsg_launch_count(void) { return dsg::g_launches.load(std::memory_order_relaxed); }
+int dsg_device_ok(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    dsg::set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return DSG_ERR_CUDA;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return (major == 10 && minor == 0) ? 1 : 0;
+}
+}

@@ -1,0 +1,111 @@
+// temb.cu — timestep embedding path in two launches (upstream: ~50 tiny cuBLAS launches per step).
+// Replaces diffusers 0.20.0 models/embeddings.py get_timestep_embedding + TimestepEmbedding and every
+// ResnetBlock2D.time_emb_proj(SiLU(emb)).  fp32 weights, fp32 math.
+#include "common.cuh"
+
+namespace dsg {
+
+constexpr int TE_THREADS = 256;
+
+// grid = batch.  emb_ws[b][:] = SiLU(linear_2(SiLU(linear_1(sinusoid(t[b])))))
+__global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __restrict__ t,
+                                                              const float* __restrict__ freqs, int half, int flip,
+                                                              const float* __restrict__ w1, const float* __restrict__ b1,
+                                                              const float* __restrict__ w2, const float* __restrict__ b2,
+                                                              int hidden, float* __restrict__ emb_ws) {
+  extern __shared__ float sm[];
+  float* e = sm;               // [2*half]
+  float* h1 = sm + 2 * half;   // [hidden]
+  const int b = blockIdx.x, in_dim = 2 * half;
+  const float tv = t[b];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float arg = __fmul_rn(tv, freqs[i]);
+    const float s = sinf(arg), c = cosf(arg);
+    // upstream: cat([sin, cos]); flip_sin_to_cos swaps the halves
+    e[flip ? half + i : i] = s;
+    e[flip ? i : half + i] = c;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < hidden; r += nwarp) {
+    float acc = 0.f;
+    for (int k = lane; k < in_dim; k += 32) acc = fmaf(w1[(int64_t)r * in_dim + k], e[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float y = acc + b1[r];
+      h1[r] = y / (1.0f + expf(-y));
+    }
+  }
+  __syncthreads();
+  for (int r = warp; r < hidden; r += nwarp) {
+    float acc = 0.f;
+    for (int k = lane; k < hidden; k += 32) acc = fmaf(w2[(int64_t)r * hidden + k], h1[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float y = acc + b2[r];
+      emb_ws[(int64_t)b * hidden + r] = y / (1.0f + expf(-y));
+    }
+  }
+}
+
+// one warp per projection row; out[b][r] = bp[r] + <wp[r], semb[b]>
+constexpr int TP_BT = 16;  // batch tile staged in shared memory
+__global__ void __launch_bounds__(TE_THREADS) temb_proj_kernel(const float* __restrict__ semb,
+                                                               const float* __restrict__ wp,
+                                                               const float* __restrict__ bp, int hidden,
+                                                               int proj_total, float* __restrict__ out, int batch) {
+  extern __shared__ float sm[];  // [TP_BT][hidden]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int r = blockIdx.x * nwarp + warp;
+  for (int b0 = 0; b0 < batch; b0 += TP_BT) {
+    const int nb = min(TP_BT, batch - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * hidden; i += blockDim.x) sm[i] = semb[(int64_t)b0 * hidden + i];
+    __syncthreads();
+    if (r < proj_total) {
+      float acc[TP_BT];
+#pragma unroll
+      for (int j = 0; j < TP_BT; ++j) acc[j] = 0.f;
+      for (int k = lane; k < hidden; k += 32) {
+        const float w = wp[(int64_t)r * hidden + k];
+#pragma unroll
+        for (int j = 0; j < TP_BT; ++j)
+          if (j < nb) acc[j] = fmaf(w, sm[j * hidden + k], acc[j]);
+      }
+      const float bias = bp[r];
+#pragma unroll
+      for (int j = 0; j < TP_BT; ++j) {
+        if (j < nb) {
+          const float v = warp_sum(acc[j]);
+          if (lane == 0) out[(int64_t)(b0 + j) * proj_total + r] = v + bias;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos,
+                              const float* w1, const float* b1, const float* w2, const float* b2, int32_t hidden,
+                              const float* wp, const float* bp, int32_t proj_total, float* emb_ws, float* out,
+                              int32_t batch, void* stream) {
+  DSG_CHECK_ARG(t && freqs && w1 && b1 && w2 && b2 && wp && bp && emb_ws && out, "dsg_time_embed: null pointer");
+  DSG_CHECK_ARG(half > 0 && hidden > 0 && hidden <= 2048 && proj_total > 0 && batch >= 0,
+                "dsg_time_embed: bad sizes");
+  if (batch == 0) return DSG_OK;
+  const size_t sm1 = (size_t)(2 * half + hidden) * sizeof(float);
+  temb_mlp_kernel<<<batch, TE_THREADS, sm1, (cudaStream_t)stream>>>(t, freqs, half, flip_sin_to_cos, w1, b1, w2, b2,
+                                                                    hidden, emb_ws);
+  DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/mlp");
+  const size_t sm2 = (size_t)TP_BT * hidden * sizeof(float);
+  if (sm2 > 48 * 1024)
+    cudaFuncSetAttribute(temb_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  const int rows_per_cta = TE_THREADS / 32;
+  temb_proj_kernel<<<ceil_div(proj_total, rows_per_cta), TE_THREADS, sm2, (cudaStream_t)stream>>>(
+      emb_ws, wp, bp, hidden, proj_total, out, batch);
+  DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/proj");
+  return DSG_OK;
+}

@@ -1,0 +1,421 @@
+"""UNetEngine — schedules the U-Net forward as a flat program of libdsg_b200 calls.
+
+Host-side orchestration only: every arithmetic step of ``UNet2DModel.forward`` (diffusers 0.20.0
+``models/unet_2d.py``; reference call sites ``DriveSceneGen/pipeline/training_pipeline.py:84`` and, through
+``DDPMPipeline.__call__``, ``DriveSceneGen/scripts/generation.py:14``) runs in the sm_100a kernels behind the C ABI of
+``include/dsg_b200.h``.  PyTorch is used for device memory and streams.  The program for one input shape is built once
+(static buffers, static pointers), so it can be replayed eagerly or captured in a CUDA graph.
+
+Data layout: activations are NHWC fp16; model input/output are NCHW fp32 (the reference's layout).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, DsgError, check
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _Arena:
+    """Named persistent device buffers; a name requested again with a larger size is re-allocated."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.retired: List[torch.Tensor] = []  # outgrown buffers stay alive: older programs hold raw pointers
+
+    def get(self, name: str, numel: int, dtype) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None:
+                self.retired.append(t)
+            t = torch.empty(max(numel, 1), dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t[:numel]
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in list(self.bufs.values()) + self.retired)
+
+
+class UNetEngine:
+    """Packed weights + per-shape execution programs for one ``UNet2DModel`` configuration."""
+
+    def __init__(self, config: dict, device: torch.device):
+        self.lib = _lib.load()
+        self.cfg = dict(config)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise DsgError("UNetEngine needs a CUDA device (there is no CPU fallback)")
+        boc = list(self.cfg["block_out_channels"])
+        for c in boc:
+            if c % 64 != 0:
+                raise DsgError(f"block_out_channels must be multiples of 64 for the tcgen05 path, got {boc}")
+        if self.cfg.get("mid_block_scale_factor", 1) != 1:
+            raise DsgError("mid_block_scale_factor != 1 is not supported")
+        if self.cfg.get("center_input_sample", False):
+            raise DsgError("center_input_sample=True is not supported")
+        self.groups = int(self.cfg.get("norm_num_groups", 32))
+        self.eps = float(self.cfg.get("norm_eps", 1e-5))
+        self.arena = _Arena(self.device)
+        self.weights: Dict[str, torch.Tensor] = {}
+        self.programs: Dict[Tuple[int, int, int], "_Program"] = {}
+        self.packed = False
+        self.conv_impl = 0       # 0 = tcgen05 igemm, 1 = plain CUDA cross-check kernel (tests only)
+        self.block_n_override = 0
+        self._build_topology()
+
+    # ------------------------------------------------------------------ topology (mirrors upstream __init__)
+    def _build_topology(self):
+        cfg = self.cfg
+        boc = list(cfg["block_out_channels"])
+        lpb = int(cfg.get("layers_per_block", 2))
+        hd = cfg.get("attention_head_dim", 8)
+        self.temb_hidden = boc[0] * 4
+        self.time_dim = boc[0]
+        resnets: List[dict] = []   # every ResnetBlock2D in execution order, with its state-dict prefix
+        self.down = []
+        out_ch = boc[0]
+        for i, t in enumerate(cfg["down_block_types"]):
+            in_ch, out_ch = out_ch, boc[i]
+            attn = t == "AttnDownBlock2D"
+            if t not in ("DownBlock2D", "AttnDownBlock2D"):
+                raise ValueError(f"{t} does not exist.")
+            blk = {"resnets": [], "attn": [], "down": i != len(boc) - 1, "ch": out_ch, "prefix": f"down_blocks.{i}"}
+            for j in range(lpb):
+                r = {"prefix": f"down_blocks.{i}.resnets.{j}", "cin": in_ch if j == 0 else out_ch, "cskip": 0,
+                     "cout": out_ch}
+                blk["resnets"].append(r)
+                resnets.append(r)
+                if attn:
+                    blk["attn"].append({"prefix": f"down_blocks.{i}.attentions.{j}", "ch": out_ch,
+                                        "head_dim": hd if hd is not None else out_ch})
+            self.down.append(blk)
+        mid_ch = boc[-1]
+        self.mid = {"resnets": [], "attn": None}
+        for j in range(2):
+            r = {"prefix": f"mid_block.resnets.{j}", "cin": mid_ch, "cskip": 0, "cout": mid_ch}
+            self.mid["resnets"].append(r)
+            resnets.append(r)
+        if cfg.get("add_attention", True):
+            self.mid["attn"] = {"prefix": "mid_block.attentions.0", "ch": mid_ch,
+                                "head_dim": hd if hd is not None else mid_ch}
+        self.up = []
+        rev = list(reversed(boc))
+        out_ch = rev[0]
+        for i, t in enumerate(cfg["up_block_types"]):
+            if t not in ("UpBlock2D", "AttnUpBlock2D"):
+                raise ValueError(f"{t} does not exist.")
+            prev, out_ch = out_ch, rev[i]
+            in_ch = rev[min(i + 1, len(boc) - 1)]
+            attn = t == "AttnUpBlock2D"
+            blk = {"resnets": [], "attn": [], "up": i != len(boc) - 1, "ch": out_ch, "prefix": f"up_blocks.{i}"}
+            for j in range(lpb + 1):
+                skip = in_ch if j == lpb else out_ch
+                r_in = prev if j == 0 else out_ch
+                r = {"prefix": f"up_blocks.{i}.resnets.{j}", "cin": r_in, "cskip": skip, "cout": out_ch}
+                blk["resnets"].append(r)
+                resnets.append(r)
+                if attn:
+                    blk["attn"].append({"prefix": f"up_blocks.{i}.attentions.{j}", "ch": out_ch,
+                                        "head_dim": hd if hd is not None else out_ch})
+            self.up.append(blk)
+        off = 0
+        for r in resnets:
+            r["temb_off"] = off
+            off += r["cout"]
+        self.resnets = resnets
+        self.proj_total = off
+        self.n_levels = len(boc)
+
+    # ------------------------------------------------------------------ weights
+    def _pack_conv(self, name: str, mode: int, w: torch.Tensor, w_sc: Optional[torch.Tensor] = None):
+        w = w.detach().to(self.device, torch.float32).contiguous()
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        csc = 0
+        if w_sc is not None:
+            w_sc = w_sc.detach().to(self.device, torch.float32).reshape(cout, -1).contiguous()
+            csc = int(w_sc.shape[1])
+        k = self.lib.dsg_packed_k(mode, cin, csc)
+        rows = self.lib.dsg_packed_rows(mode, cout)
+        out = torch.empty(rows * k, dtype=torch.float16, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.dsg_pack_conv_weight(mode, w.data_ptr(), cout, cin, _p(w_sc), csc, out.data_ptr(), st),
+              f"pack {name}")
+        self.weights[name] = out
+
+    def _f32(self, name: str, t: torch.Tensor):
+        self.weights[name] = t.detach().to(self.device, torch.float32).contiguous().clone()
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """(Re)pack all weights from a state dict with upstream key names."""
+        with torch.cuda.device(self.device):
+            self._f32("conv_in.w", sd["conv_in.weight"])
+            self._f32("conv_in.b", sd["conv_in.bias"])
+            self._f32("conv_out.w", sd["conv_out.weight"])
+            self._f32("conv_out.b", sd["conv_out.bias"])
+            self._f32("norm_out.g", sd["conv_norm_out.weight"])
+            self._f32("norm_out.b", sd["conv_norm_out.bias"])
+            for k in ("linear_1", "linear_2"):
+                self._f32(f"te.{k}.w", sd[f"time_embedding.{k}.weight"])
+                self._f32(f"te.{k}.b", sd[f"time_embedding.{k}.bias"])
+            self._f32("te.proj.w", torch.cat([sd[r["prefix"] + ".time_emb_proj.weight"] for r in self.resnets], 0))
+            self._f32("te.proj.b", torch.cat([sd[r["prefix"] + ".time_emb_proj.bias"] for r in self.resnets], 0))
+            half = self.time_dim // 2
+            # exp table computed on the host exactly like upstream get_timestep_embedding (models/embeddings.py)
+            exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
+            exponent = exponent / (half - float(self.cfg.get("freq_shift", 0)))
+            self._f32("te.freqs", torch.exp(exponent))
+            for r in self.resnets:
+                pre = r["prefix"]
+                for nm in ("norm1", "norm2"):
+                    self._f32(f"{pre}.{nm}.g", sd[f"{pre}.{nm}.weight"])
+                    self._f32(f"{pre}.{nm}.b", sd[f"{pre}.{nm}.bias"])
+                self._pack_conv(f"{pre}.conv1", 0, sd[f"{pre}.conv1.weight"])
+                self._f32(f"{pre}.conv1.b", sd[f"{pre}.conv1.bias"])
+                sc_key = f"{pre}.conv_shortcut.weight"
+                has_sc = sc_key in sd
+                if has_sc != (r["cin"] + r["cskip"] != r["cout"]):
+                    raise DsgError(f"{pre}: conv_shortcut presence does not match channel counts")
+                self._pack_conv(f"{pre}.conv2", 0, sd[f"{pre}.conv2.weight"], sd[sc_key] if has_sc else None)
+                b2 = sd[f"{pre}.conv2.bias"].detach().to(self.device, torch.float32)
+                if has_sc:
+                    b2 = b2 + sd[f"{pre}.conv_shortcut.bias"].detach().to(self.device, torch.float32)
+                self._f32(f"{pre}.conv2.b", b2)
+                r["has_sc"] = has_sc
+            attns = [a for blk in self.down for a in blk["attn"]] + ([self.mid["attn"]] if self.mid["attn"] else []) \
+                + [a for blk in self.up for a in blk["attn"]]
+            for a in attns:
+                pre = a["prefix"]
+                self._f32(f"{pre}.gn.g", sd[f"{pre}.group_norm.weight"])
+                self._f32(f"{pre}.gn.b", sd[f"{pre}.group_norm.bias"])
+                wqkv = torch.cat([sd[f"{pre}.to_q.weight"], sd[f"{pre}.to_k.weight"], sd[f"{pre}.to_v.weight"]], 0)
+                bqkv = torch.cat([sd[f"{pre}.to_q.bias"], sd[f"{pre}.to_k.bias"], sd[f"{pre}.to_v.bias"]], 0)
+                self._pack_conv(f"{pre}.qkv", 3, wqkv)
+                self._f32(f"{pre}.qkv.b", bqkv)
+                self._pack_conv(f"{pre}.out", 3, sd[f"{pre}.to_out.0.weight"])
+                self._f32(f"{pre}.out.b", sd[f"{pre}.to_out.0.bias"])
+            for i, blk in enumerate(self.down):
+                if blk["down"]:
+                    pre = f"down_blocks.{i}.downsamplers.0.conv"
+                    self._pack_conv(pre, 1, sd[pre + ".weight"])
+                    self._f32(pre + ".b", sd[pre + ".bias"])
+            for i, blk in enumerate(self.up):
+                if blk["up"]:
+                    pre = f"up_blocks.{i}.upsamplers.0.conv"
+                    self._pack_conv(pre, 2, sd[pre + ".weight"])
+                    self._f32(pre + ".b", sd[pre + ".bias"])
+        self.packed = True
+        self.programs.clear()  # programs hold raw weight pointers
+
+    # ------------------------------------------------------------------ program construction
+    def program(self, batch: int, h: int, w: int) -> "_Program":
+        key = (batch, h, w)
+        prog = self.programs.get(key)
+        if prog is None:
+            if not self.packed:
+                raise DsgError("UNetEngine: weights have not been loaded")
+            div = 2 ** (self.n_levels - 1)
+            if h % div or w % div:
+                raise DsgError(f"input {h}x{w} must be divisible by {div}")
+            prog = _Program(self, batch, h, w)
+            self.programs[key] = prog
+        return prog
+
+    def forward(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """sample: fp32 NCHW on this device; t_float: fp32 [B] timestep values on this device."""
+        b, c, h, w = sample.shape
+        prog = self.program(b, h, w)
+        return prog.run(sample, t_float, out)
+
+
+class _Program:
+    """The flat kernel sequence of one forward pass for a fixed (batch, H, W)."""
+
+    def __init__(self, eng: UNetEngine, batch: int, h: int, w: int):
+        self.eng, self.b, self.h, self.w = eng, batch, h, w
+        self.lib = eng.lib
+        self.ops: List[Callable[[int], None]] = []
+        self.keep: list = []          # ctypes structs / tensors that must outlive the closures
+        self.uid = 0
+        self.in_ptr = C.c_void_p(0)   # set per run (or to a static buffer under graph capture)
+        self.t_ptr = C.c_void_p(0)
+        self.out_ptr = C.c_void_p(0)
+        self.cin = int(eng.cfg.get("in_channels", 3))
+        self.cout = int(eng.cfg.get("out_channels", 3))
+        # pass 1 sizes the shared temporaries (so no buffer is outgrown mid-program), pass 2 emits the ops
+        self._measure: Optional[Dict[Tuple[str, torch.dtype], int]] = {}
+        self._build()
+        for (name, dtype), numel in self._measure.items():
+            eng.arena.get(name, numel, dtype)
+        self._measure = None
+        self.ops, self.keep = [], []
+        self._build()
+
+    # --- buffers -------------------------------------------------------------------------------------
+    def _new(self, name: str, hw: Tuple[int, int], ch: int) -> torch.Tensor:
+        numel = self.b * hw[0] * hw[1] * ch
+        return self.eng.arena.get(f"{self.b}x{self.h}x{self.w}/{name}", numel, torch.float16)
+
+    def _tmp_raw(self, name: str, numel: int, dtype) -> torch.Tensor:
+        # temporaries are shared by name across layers (and shapes): sized to the largest request
+        if self._measure is not None:
+            key = (f"tmp/{name}", dtype)
+            self._measure[key] = max(self._measure.get(key, 0), numel)
+            return self.eng.arena.get("tmp/_measure", 16, dtype)
+        return self.eng.arena.get(f"tmp/{name}", numel, dtype)
+
+    def _tmp(self, name: str, hw: Tuple[int, int], ch: int) -> torch.Tensor:
+        return self._tmp_raw(name, self.b * hw[0] * hw[1] * ch, torch.float16)
+
+    # --- op emitters ---------------------------------------------------------------------------------
+    def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out):
+        eng, lib, b = self.eng, self.lib, self.b
+        npx = hw[0] * hw[1]
+        chunks = lib.dsg_gn_chunks(npx)
+        part = self._tmp_raw("gn_partial", b * chunks * eng.groups * 2, torch.float32)
+        g, bt = eng.weights[gname], eng.weights[bname]
+        a1 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), b, npx, eng.groups)
+        a2 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), g.data_ptr(), bt.data_ptr(), eng.eps, act, out.data_ptr(), b,
+              npx, eng.groups)
+        self.ops.append(lambda st, a=a1: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
+        self.ops.append(lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
+
+    def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
+              sc2=None, csc2=0):
+        eng, lib = self.eng, self.lib
+        a = ConvArgs()
+        a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, self.b, hw[0], hw[1], cin, cout
+        a.x = x.data_ptr()
+        a.sc1, a.csc1, a.sc2, a.csc2 = _p(sc1), csc1, _p(sc2), csc2
+        a.wpacked = eng.weights[wname].data_ptr()
+        a.bias = eng.weights[bname].data_ptr()
+        if temb_off is not None:
+            a.temb, a.temb_stride, a.temb_off = self.temb.data_ptr(), eng.proj_total, temb_off
+        a.residual = _p(residual)
+        a.out = out.data_ptr()
+        a.block_n = eng.block_n_override if (eng.block_n_override and cout % eng.block_n_override == 0) else 0
+        a.impl = eng.conv_impl
+        self.keep.append(a)
+        ref = C.byref(a)
+        self.ops.append(lambda st, r=ref: check(lib.dsg_conv(r, st), f"conv {wname}"))
+
+    def _resnet(self, r, x1, x2, hw, out):
+        c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
+        act = self._tmp("act", hw, c1 + c2)
+        self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
+        hbuf = self._tmp("h", hw, co)
+        self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"])
+        act2 = self._tmp("act", hw, co)
+        self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2)
+        if r["has_sc"]:
+            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2)
+        else:
+            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, residual=x1)
+
+    def _attn(self, a, x, hw, out):
+        eng, lib, b = self.eng, self.lib, self.b
+        ch, pre, hd = a["ch"], a["prefix"], a["head_dim"]
+        act = self._tmp("act", hw, ch)
+        self._gn(x, ch, None, 0, hw, f"{pre}.gn.g", f"{pre}.gn.b", 0, act)
+        qkv = self._tmp("qkv", hw, 3 * ch)
+        self._conv(3, act, hw, ch, 3 * ch, f"{pre}.qkv", f"{pre}.qkv.b", qkv)
+        o = self._tmp("attn_o", hw, ch)
+        args = (qkv.data_ptr(), o.data_ptr(), b, hw[0] * hw[1], ch // hd, hd)
+        self.ops.append(lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
+        self._conv(3, o, hw, ch, ch, f"{pre}.out", f"{pre}.out.b", out, residual=x)
+
+    # --- whole forward -------------------------------------------------------------------------------
+    def _build(self):
+        eng, lib, b = self.eng, self.lib, self.b
+        W = eng.weights
+        hw = (self.h, self.w)
+        self.temb = eng.arena.get(f"{b}/temb", b * eng.proj_total, torch.float32)
+        emb_ws = eng.arena.get(f"{b}/emb_ws", b * eng.temb_hidden, torch.float32)
+        half = eng.time_dim // 2
+        flip = 1 if eng.cfg.get("flip_sin_to_cos", True) else 0
+        te_args = (W["te.freqs"].data_ptr(), half, flip, W["te.linear_1.w"].data_ptr(), W["te.linear_1.b"].data_ptr(),
+                   W["te.linear_2.w"].data_ptr(), W["te.linear_2.b"].data_ptr(), eng.temb_hidden,
+                   W["te.proj.w"].data_ptr(), W["te.proj.b"].data_ptr(), eng.proj_total, emb_ws.data_ptr(),
+                   self.temb.data_ptr(), b)
+        self.ops.append(lambda st: check(lib.dsg_time_embed(self.t_ptr, *te_args, st), "time_embed"))
+        c0 = eng.cfg["block_out_channels"][0]
+        x = self._new("conv_in", hw, c0)
+        ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(), b, self.cin, hw[0], hw[1], c0)
+        self.ops.append(lambda st: check(lib.dsg_conv_in(self.in_ptr, *ci_args, st), "conv_in"))
+        skips = [(x, c0, hw)]
+        for i, blk in enumerate(eng.down):
+            for j, r in enumerate(blk["resnets"]):
+                has_attn = bool(blk["attn"])
+                out = self._new(f"d{i}r{j}" + ("pre" if has_attn else ""), hw, r["cout"])
+                self._resnet(r, x, None, hw, out)
+                x = out
+                if has_attn:
+                    out = self._new(f"d{i}a{j}", hw, r["cout"])
+                    self._attn(blk["attn"][j], x, hw, out)
+                    x = out
+                skips.append((x, r["cout"], hw))
+            if blk["down"]:
+                nhw = (hw[0] // 2, hw[1] // 2)
+                out = self._new(f"d{i}ds", nhw, blk["ch"])
+                pre = f"down_blocks.{i}.downsamplers.0.conv"
+                self._conv(1, x, hw, blk["ch"], blk["ch"], pre, pre + ".b", out)
+                x, hw = out, nhw
+                skips.append((x, blk["ch"], hw))
+        mid = eng.mid
+        out = self._new("m0", hw, mid["resnets"][0]["cout"])
+        self._resnet(mid["resnets"][0], x, None, hw, out)
+        x = out
+        if mid["attn"] is not None:
+            out = self._new("ma", hw, mid["attn"]["ch"])
+            self._attn(mid["attn"], x, hw, out)
+            x = out
+        out = self._new("m1", hw, mid["resnets"][1]["cout"])
+        self._resnet(mid["resnets"][1], x, None, hw, out)
+        x = out
+        for i, blk in enumerate(eng.up):
+            for j, r in enumerate(blk["resnets"]):
+                sk, sk_c, sk_hw = skips.pop()
+                assert sk_c == r["cskip"] and sk_hw == hw, (sk_c, r["cskip"], sk_hw, hw)
+                has_attn = bool(blk["attn"])
+                out = self._new(f"u{i}r{j}" + ("pre" if has_attn else ""), hw, r["cout"])
+                self._resnet(r, x, sk, hw, out)
+                x = out
+                if has_attn:
+                    out = self._new(f"u{i}a{j}", hw, r["cout"])
+                    self._attn(blk["attn"][j], x, hw, out)
+                    x = out
+            if blk["up"]:
+                nhw = (hw[0] * 2, hw[1] * 2)
+                out = self._new(f"u{i}us", nhw, blk["ch"])
+                pre = f"up_blocks.{i}.upsamplers.0.conv"
+                self._conv(2, x, hw, blk["ch"], blk["ch"], pre, pre + ".b", out)
+                x, hw = out, nhw
+        assert not skips
+        act = self._tmp("act", hw, c0)
+        self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
+        co_args = (act.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
+        co_tail = (b, c0, hw[0], hw[1], self.cout)
+        self.ops.append(lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
+        self.n_launches = len(self.ops) + 1  # time_embed is two launches
+
+    def run(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if sample.dtype != torch.float32 or not sample.is_contiguous():
+            sample = sample.contiguous().float()
+        if out is None:
+            out = torch.empty((self.b, self.cout, self.h, self.w), dtype=torch.float32, device=sample.device)
+        assert t_float.dtype == torch.float32 and t_float.numel() == self.b and t_float.is_cuda
+        self.in_ptr = C.c_void_p(sample.data_ptr())
+        self.t_ptr = C.c_void_p(t_float.data_ptr())
+        self.out_ptr = C.c_void_p(out.data_ptr())
+        st = torch.cuda.current_stream(sample.device).cuda_stream
+        for op in self.ops:
+            op(st)
+        return out

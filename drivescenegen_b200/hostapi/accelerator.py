@@ -1,0 +1,320 @@
+"""``accelerate.Accelerator`` / ``notebook_launcher`` mirror — the only distributed component of the reference.
+
+Reference call sites (DriveSceneGen/pipeline/training_pipeline.py): ctor :48-53, ``is_main_process`` :54,100,
+``init_trackers`` :56, ``prepare`` :59, ``is_local_main_process`` :67, ``accumulate`` :82, ``backward`` :86,
+``clip_grad_norm_`` :88, ``log`` :96, ``unwrap_model`` :101; ``notebook_launcher(fn, args, num_processes=1)``
+DriveSceneGen/scripts/train.py:122.  Semantics restated from accelerate 0.22.0 in SURVEY.md App. B.4.
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE).  Data parallelism is ONE all-reduce per step over a
+single flat gradient buffer (NCCL over NVLink/NVSwitch; gloo on CPU for the tests), issued from ``backward``; the mean
+(1/world) is folded into the same pass.  No DistributedDataParallel wrapper, so ``unwrap_model`` is the identity.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class AcceleratedOptimizer:
+    def __init__(self, optimizer, accelerator: "Accelerator"):
+        self.optimizer = optimizer
+        self.accelerator = accelerator
+        self.step_was_skipped = False
+
+    @property
+    def param_groups(self):
+        return self.optimizer.param_groups
+
+    @property
+    def state(self):
+        return self.optimizer.state
+
+    def state_dict(self):
+        return self.optimizer.state_dict()
+
+    def load_state_dict(self, sd):
+        self.optimizer.load_state_dict(sd)
+
+    def zero_grad(self, set_to_none: Optional[bool] = None):
+        if self.accelerator.sync_gradients:
+            if set_to_none is None:
+                self.optimizer.zero_grad()
+            else:
+                self.optimizer.zero_grad(set_to_none=set_to_none)
+
+    def step(self, closure=None):
+        acc = self.accelerator
+        if not acc.sync_gradients:
+            return
+        if acc.scaler is not None:
+            before = acc.scaler.get_scale()
+            acc.scaler.step(self.optimizer, closure) if closure is not None else acc.scaler.step(self.optimizer)
+            acc.scaler.update()
+            self.step_was_skipped = acc.scaler.get_scale() < before
+        else:
+            self.optimizer.step(closure) if closure is not None else self.optimizer.step()
+            self.step_was_skipped = False
+
+
+class AcceleratedScheduler:
+    def __init__(self, scheduler, optimizers: List[AcceleratedOptimizer], accelerator: "Accelerator"):
+        self.scheduler = scheduler
+        self.optimizers = optimizers
+        self.accelerator = accelerator
+
+    def step(self, *args, **kwargs):
+        acc = self.accelerator
+        if not acc.sync_gradients:
+            return
+        if any(o.step_was_skipped for o in self.optimizers):
+            return
+        # upstream: when batches are not split across ranks the wrapped scheduler advances num_processes times
+        for _ in range(acc.num_processes if not acc.split_batches else 1):
+            self.scheduler.step(*args, **kwargs)
+
+    def get_last_lr(self):
+        return self.scheduler.get_last_lr()
+
+    def state_dict(self):
+        return self.scheduler.state_dict()
+
+    def load_state_dict(self, sd):
+        self.scheduler.load_state_dict(sd)
+
+    def __getattr__(self, name):
+        return getattr(self.scheduler, name)
+
+
+class ShardedDataLoader:
+    """Rank r of N sees batches r, r+N, r+2N, ... (per-rank batch size unchanged), moved to the device."""
+
+    def __init__(self, loader, device, rank: int, world: int):
+        self.loader, self.device, self.rank, self.world = loader, device, rank, world
+
+    def __len__(self):
+        n = len(self.loader)
+        return (n + self.world - 1) // self.world if self.world > 1 else n
+
+    @property
+    def dataset(self):
+        return self.loader.dataset
+
+    @property
+    def batch_size(self):
+        return self.loader.batch_size
+
+    def _move(self, b):
+        if torch.is_tensor(b):
+            return b.to(self.device, non_blocking=True)
+        if isinstance(b, (list, tuple)):
+            return type(b)(self._move(x) for x in b)
+        if isinstance(b, dict):
+            return {k: self._move(v) for k, v in b.items()}
+        return b
+
+    def __iter__(self):
+        if self.world == 1:
+            for b in self.loader:
+                yield self._move(b)
+            return
+        # every rank must run the same number of steps: the tail is padded by wrapping around (even_batches=True)
+        batches, first = [], []
+        for i, b in enumerate(self.loader):
+            if len(first) < self.world:
+                first.append(b)
+            batches.append(b)
+            if len(batches) == self.world:
+                yield self._move(batches[self.rank])
+                batches = []
+        if batches:
+            while len(batches) < self.world:
+                batches.append(first[len(batches) % len(first)])
+            yield self._move(batches[self.rank])
+
+
+class Accelerator:
+    def __init__(self, mixed_precision: Optional[str] = None, gradient_accumulation_steps: int = 1,
+                 log_with=None, project_dir: Optional[str] = None, split_batches: bool = False, cpu: bool = False,
+                 **kwargs):
+        self.mixed_precision = (mixed_precision or os.environ.get("ACCELERATE_MIXED_PRECISION", "no")).lower()
+        if self.mixed_precision not in ("no", "fp16", "bf16"):
+            raise ValueError(f"Unknown mixed_precision mode: {self.mixed_precision}")
+        self.gradient_accumulation_steps = int(gradient_accumulation_steps)
+        self.log_with = log_with
+        self.project_dir = project_dir
+        self.split_batches = split_batches
+        self.process_index = int(os.environ.get("RANK", "0"))
+        self.local_process_index = int(os.environ.get("LOCAL_RANK", "0"))
+        self.num_processes = int(os.environ.get("WORLD_SIZE", "1"))
+        use_cuda = torch.cuda.is_available() and not cpu
+        self.device = torch.device("cuda", self.local_process_index) if use_cuda else torch.device("cpu")
+        if use_cuda:
+            torch.cuda.set_device(self.device)
+        if self.num_processes > 1 and not dist.is_initialized():
+            dist.init_process_group(backend="nccl" if use_cuda else "gloo")
+        self.scaler = None
+        if self.mixed_precision == "fp16" and use_cuda:
+            self.scaler = torch.amp.GradScaler("cuda")
+        self.sync_gradients = True
+        self.step = 0
+        self._models: List[torch.nn.Module] = []
+        self._optimizers: List[AcceleratedOptimizer] = []
+        self._flat_grad: Optional[torch.Tensor] = None
+        self.trackers = []
+        self._writer = None
+
+    # ------------------------------------------------------------------ process info
+    @property
+    def is_main_process(self) -> bool:
+        return self.process_index == 0
+
+    @property
+    def is_local_main_process(self) -> bool:
+        return self.local_process_index == 0
+
+    @property
+    def use_distributed(self) -> bool:
+        return self.num_processes > 1
+
+    def wait_for_everyone(self):
+        if self.use_distributed:
+            dist.barrier()
+
+    def print(self, *a, **k):
+        if self.is_local_main_process:
+            print(*a, **k)
+
+    # ------------------------------------------------------------------ trackers
+    def init_trackers(self, project_name: str, config: Optional[dict] = None, init_kwargs: dict = {}):
+        if not self.is_main_process or self.log_with is None:
+            return
+        if self.log_with not in ("tensorboard", "all") and "tensorboard" not in str(self.log_with):
+            return
+        from torch.utils.tensorboard import SummaryWriter
+        logdir = os.path.join(self.project_dir or ".", project_name)
+        os.makedirs(logdir, exist_ok=True)
+        self._writer = SummaryWriter(logdir)
+
+    def log(self, values: dict, step: Optional[int] = None, log_kwargs: dict = {}):
+        if self._writer is None:
+            return
+        for k, v in values.items():
+            if isinstance(v, (int, float)):
+                self._writer.add_scalar(k, v, global_step=step)
+            elif isinstance(v, str):
+                self._writer.add_text(k, v, global_step=step)
+        self._writer.flush()
+
+    def end_training(self):
+        if self._writer is not None:
+            self._writer.close()
+            self._writer = None
+
+    # ------------------------------------------------------------------ prepare
+    def prepare(self, *args):
+        out = []
+        for obj in args:
+            if isinstance(obj, torch.nn.Module):
+                out.append(self.prepare_model(obj))
+            elif isinstance(obj, torch.optim.Optimizer):
+                o = AcceleratedOptimizer(obj, self)
+                self._optimizers.append(o)
+                out.append(o)
+            elif isinstance(obj, torch.utils.data.DataLoader):
+                out.append(ShardedDataLoader(obj, self.device, self.process_index, self.num_processes))
+            elif isinstance(obj, torch.optim.lr_scheduler.LRScheduler):
+                out.append(("__sched__", obj))
+            else:
+                out.append(obj)
+        out = [AcceleratedScheduler(o[1], self._optimizers, self) if isinstance(o, tuple) and o and o[0] == "__sched__"
+               else o for o in out]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def prepare_model(self, model: torch.nn.Module):
+        model = model.to(self.device)
+        if self.use_distributed:
+            # replicas start identical: broadcast rank 0's parameters/buffers once
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0)
+        self._models.append(model)
+        return model
+
+    def unwrap_model(self, model, keep_fp32_wrapper: bool = True):
+        return model
+
+    # ------------------------------------------------------------------ training step plumbing
+    @contextlib.contextmanager
+    def accumulate(self, *models):
+        self.step += 1
+        self.sync_gradients = (self.step % self.gradient_accumulation_steps) == 0
+        yield
+
+    @contextlib.contextmanager
+    def autocast(self):
+        if self.device.type == "cuda" and self.mixed_precision in ("fp16", "bf16"):
+            dt = torch.float16 if self.mixed_precision == "fp16" else torch.bfloat16
+            with torch.autocast("cuda", dtype=dt):
+                yield
+        else:
+            yield
+
+    def _allreduce_grads(self):
+        """ONE all-reduce over a single flat gradient buffer, averaged over ranks."""
+        params = [p for m in self._models for p in m.parameters() if p.grad is not None]
+        if not params:
+            return
+        total = sum(p.grad.numel() for p in params)
+        if self._flat_grad is None or self._flat_grad.numel() != total or self._flat_grad.device != params[0].device:
+            self._flat_grad = torch.empty(total, dtype=torch.float32, device=params[0].grad.device)
+        flat = self._flat_grad
+        views = []
+        off = 0
+        for p in params:
+            n = p.grad.numel()
+            views.append(flat[off:off + n].view_as(p.grad))
+            off += n
+        torch._foreach_copy_(views, [p.grad for p in params])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / self.num_processes)
+        torch._foreach_copy_([p.grad for p in params], views)
+
+    def backward(self, loss: torch.Tensor, **kwargs):
+        loss = loss / self.gradient_accumulation_steps
+        if self.scaler is not None:
+            self.scaler.scale(loss).backward(**kwargs)
+        else:
+            loss.backward(**kwargs)
+        if self.use_distributed and self.sync_gradients:
+            self._allreduce_grads()
+
+    def unscale_gradients(self):
+        if self.scaler is not None:
+            for o in self._optimizers:
+                self.scaler.unscale_(o.optimizer)
+
+    def clip_grad_norm_(self, parameters: Iterable[torch.Tensor], max_norm: float, norm_type: float = 2):
+        self.unscale_gradients()
+        return torch.nn.utils.clip_grad_norm_(parameters, max_norm, norm_type=norm_type)
+
+    def gather(self, tensor: torch.Tensor):
+        if not self.use_distributed:
+            return tensor
+        outs = [torch.empty_like(tensor) for _ in range(self.num_processes)]
+        dist.all_gather(outs, tensor.contiguous())
+        return torch.cat(outs, dim=0)
+
+
+def notebook_launcher(function, args=(), num_processes=None, mixed_precision="no", use_port="29500", **kwargs):
+    """upstream with num_processes=1 (the reference's setting): banner + in-process call.  Multi-GPU runs launch the
+    script under torchrun; each rank's ``Accelerator()`` reads RANK / LOCAL_RANK / WORLD_SIZE."""
+    if num_processes is not None and num_processes > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        raise NotImplementedError("dsg_b200: launch multi-GPU training with torchrun "
+                                  "(python -m torch.distributed.run --nproc-per-node N script.py)")
+    dev = "GPU" if torch.cuda.is_available() else "CPU"
+    print(f"Launching training on one {dev}." if int(os.environ.get("WORLD_SIZE", "1")) == 1
+          else f"Launching training on {os.environ['WORLD_SIZE']} processes.")
+    function(*args)

@@ -1,0 +1,131 @@
+/*
+ * dsg_b200.h — C ABI of libdsg_b200.so, the sm_100a denoising engine behind the `diffusers` call surface
+ * used by SS47816/DriveSceneGen.
+ *
+ * The reference has NO native FFI for this path: the boundary it binds is the Python import surface of
+ * diffusers==0.20.0 / accelerate==0.22.0 (requirements.txt:15-16).  Each entry point below names the upstream
+ * operation it replaces and the reference call site that reaches it (paths relative to /root/reference):
+ *   UNet2DModel.forward     DriveSceneGen/pipeline/training_pipeline.py:84, DriveSceneGen/scripts/generation.py:14
+ *   DDPMScheduler.step      DriveSceneGen/pipeline/training_pipeline.py:26-32, DriveSceneGen/scripts/generation.py:14-20
+ *   DDPMScheduler.add_noise DriveSceneGen/pipeline/training_pipeline.py:80
+ *   pipeline post-process   DriveSceneGen/scripts/generation.py:22-24 ((x/2+.5).clamp(0,1) -> NHWC -> uint8)
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; dsg_last_error() gives a thread-local message.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library never allocates, frees or
+ *     retains caller memory, never synchronises the host, and launches on the given stream, so every call is
+ *     legal under CUDA-graph stream capture.
+ *   - activations between U-Net ops are NHWC fp16 ("h16"): [N][H][W][C], C a multiple of 64, base pointers
+ *     16-byte aligned.  Model input / output and the schedulers work on NCHW fp32 like the reference.
+ *   - stream is a cudaStream_t passed as void*.
+ */
+#ifndef DSG_B200_H_
+#define DSG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSG_OK 0
+#define DSG_ERR_INVALID (-1)
+#define DSG_ERR_CUDA (-2)
+#define DSG_ERR_UNSUPPORTED (-3)
+
+int dsg_version(void);
+const char* dsg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
+int64_t dsg_launch_count(void);
+/* 1 if the current device is sm_100 (tcgen05/TMA kernels can run), 0 otherwise, <0 on error */
+int dsg_device_ok(void);
+
+/* ---------------------------------------------------------------- schedulers (fp32, NCHW, elementwise) ----
+ * coef_table: device float[rows][8]; row r =
+ *   { sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt, sigma, clip_range, has_noise(0/1), unused }     (DDPM)
+ *   { sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), dir_coef, sigma, clip_range, has_noise, unused } (DDIM)
+ * The row is row_dev ? *row_dev : row (a device-side index keeps one captured graph valid for every step).
+ * Arithmetic order follows upstream scheduling_ddpm.py::step / scheduling_ddim.py::step exactly, with every
+ * product and sum rounded separately (no FMA contraction), so results are bit-identical to the fp32 CPU path. */
+int dsg_ddpm_step(const float* eps, const float* sample, const float* noise /* may be NULL */, float* prev,
+                  int64_t numel, const float* coef_table, const int32_t* row_dev, int32_t row, void* stream);
+int dsg_ddim_step(const float* eps, const float* sample, const float* noise /* may be NULL */, float* prev,
+                  int64_t numel, const float* coef_table, const int32_t* row_dev, int32_t row, void* stream);
+/* DDPMScheduler.add_noise: out = sqrt_ac[t[n]] * x0 + sqrt_1mac[t[n]] * noise ; t is int64[batch] */
+int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+                  const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, void* stream);
+/* pipeline post-process: NCHW fp32 latent -> NHWC; u8 = round(clamp(x/2+.5,0,1)*255) (numpy_to_pil) and/or
+ * f32 = clamp(x/2+.5,0,1).  Either output may be NULL. */
+int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, int32_t n, int32_t c, int32_t h,
+                        int32_t w, void* stream);
+
+/* ---------------------------------------------------------------- U-Net building blocks ------------------- */
+/* Timesteps + TimestepEmbedding + all per-ResnetBlock time_emb_proj in two launches.
+ *   t: float[batch] (timestep values), freqs: float[half] (exp table, host-computed like upstream),
+ *   w1 [hidden][2*half], b1, w2 [hidden][hidden], b2, wp [proj_total][hidden], bp [proj_total]  (all fp32)
+ *   emb_ws: float[batch][hidden] scratch; out: float[batch][proj_total] = Linear(SiLU(emb)) per block. */
+int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos, const float* w1,
+                   const float* b1, const float* w2, const float* b2, int32_t hidden, const float* wp,
+                   const float* bp, int32_t proj_total, float* emb_ws, float* out, int32_t batch, void* stream);
+
+/* conv_in: NCHW fp32 [n][cin][h][w] (cin <= 4) -> h16 [n][h][w][cout]; 3x3, pad 1.  w: fp32 [cout][cin][3][3]. */
+int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, int32_t n, int32_t cin, int32_t h,
+                int32_t wd, int32_t cout, void* stream);
+/* conv_out: h16 [n][h][w][cin] (already GroupNorm+SiLU'd) -> NCHW fp32 [n][cout][h][w] (cout <= 4). */
+int dsg_conv_out(const void* x_h16, const float* w, const float* b, float* out, int32_t n, int32_t cin, int32_t h,
+                 int32_t wd, int32_t cout, void* stream);
+
+/* GroupNorm statistics over the channel-concatenation of up to two h16 tensors (x1 has c1 channels, x2 has c2,
+ * x2 may be NULL).  partial: float[n][chunks][groups][2] shifted sums; chunks is returned by
+ * dsg_gn_chunks(hw).  Deterministic (no atomics). */
+int32_t dsg_gn_chunks(int64_t hw);
+int dsg_gn_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, float* partial, int32_t n, int64_t hw,
+                 int32_t groups, void* stream);
+/* y = act(GroupNorm(cat(x1,x2))) written as ONE h16 tensor with c1+c2 channels; act: 0 none, 1 SiLU. */
+int dsg_gn_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* partial, const float* gamma,
+                 const float* beta, float eps, int32_t act, void* y, int32_t n, int64_t hw, int32_t groups,
+                 void* stream);
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMA -> smem -> UMMA -> TMEM -> epilogue).
+ * mode: 0 = 3x3 stride 1 pad 1, 1 = 3x3 stride 2 pad 1, 2 = nearest-2x upsample followed by 3x3 pad 1
+ *       (evaluated as four 2x2 sub-pixel convolutions on pre-summed weights), 3 = 1x1.
+ * x: h16 [n][h][w][cin].  sc1/sc2: optional extra 1x1 ("conv_shortcut") inputs at the OUTPUT resolution whose
+ * channels are appended to the GEMM K dimension (sc2 may be NULL; csc2 = 0).  residual: optional h16 tensor shaped
+ * like the output, added in the epilogue.  bias: float[cout].  temb: optional float[n][temb_stride], element
+ * [n][temb_off + c] is added to output channel c.  wpacked: h16, layout produced by dsg_pack_conv_weight.
+ * out: h16 [n][oh][ow][cout]. */
+typedef struct dsg_conv_args {
+  int32_t mode;
+  int32_t n, h, w, cin, cout;
+  const void* x;
+  const void* sc1;
+  int32_t csc1;
+  const void* sc2;
+  int32_t csc2;
+  const void* wpacked;
+  const float* bias;
+  const float* temb;
+  int32_t temb_stride, temb_off;
+  const void* residual;
+  void* out;
+  int32_t block_n; /* 0 = auto, else 64/128/256 */
+  int32_t impl;    /* 0 = tcgen05 path, 1 = plain CUDA-core cross-check kernel (slow; debugging/tests only) */
+} dsg_conv_args;
+int dsg_conv(const dsg_conv_args* args, void* stream);
+/* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */
+int64_t dsg_packed_k(int32_t mode, int32_t cin, int32_t csc);
+int64_t dsg_packed_rows(int32_t mode, int32_t cout);
+/* Pack fp32 OIHW conv weights (+ optional 1x1 shortcut weights [cout][csc]) into the h16 GEMM layout.
+ * All pointers are device pointers. */
+int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_t cin, const float* w_sc,
+                         int32_t csc, void* wpacked, void* stream);
+
+/* Multi-head self-attention core on tokens: qkv h16 [n][tokens][3*c] (q | k | v, heads x head_dim inside each),
+ * out h16 [n][tokens][c]; softmax(q k^T / sqrt(head_dim)) v per head.  head_dim must be 8, 16, 32 or 64. */
+int dsg_attention(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSG_B200_H_ */
