@@ -131,8 +131,9 @@ extern "C" {
 
 int dsg_ddpm_step(const float* eps, const float* sample, const float* noise, float* prev, int64_t numel,
                   const float* coef_table, const int32_t* row_dev, int32_t row, void* stream) {
-  DSG_CHECK_ARG(eps && sample && prev && coef_table && numel >= 0, "dsg_ddpm_step: null pointer or negative size");
+  DSG_CHECK_ARG(numel >= 0, "dsg_ddpm_step: negative size");
   if (numel == 0) return DSG_OK;
+  DSG_CHECK_ARG(eps && sample && prev && coef_table, "dsg_ddpm_step: null pointer");
   DSG_CHECK_ARG(((uintptr_t)eps | (uintptr_t)sample | (uintptr_t)prev | (uintptr_t)noise) % 16 == 0,
                 "dsg_ddpm_step: pointers must be 16-byte aligned");
   sched_step_kernel<false><<<grid_for(numel / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -143,8 +144,9 @@ int dsg_ddpm_step(const float* eps, const float* sample, const float* noise, flo
 
 int dsg_ddim_step(const float* eps, const float* sample, const float* noise, float* prev, int64_t numel,
                   const float* coef_table, const int32_t* row_dev, int32_t row, void* stream) {
-  DSG_CHECK_ARG(eps && sample && prev && coef_table && numel >= 0, "dsg_ddim_step: null pointer or negative size");
+  DSG_CHECK_ARG(numel >= 0, "dsg_ddim_step: negative size");
   if (numel == 0) return DSG_OK;
+  DSG_CHECK_ARG(eps && sample && prev && coef_table, "dsg_ddim_step: null pointer");
   DSG_CHECK_ARG(((uintptr_t)eps | (uintptr_t)sample | (uintptr_t)prev | (uintptr_t)noise) % 16 == 0,
                 "dsg_ddim_step: pointers must be 16-byte aligned");
   sched_step_kernel<true><<<grid_for(numel / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
@@ -155,9 +157,9 @@ int dsg_ddim_step(const float* eps, const float* sample, const float* noise, flo
 
 int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
                   const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, void* stream) {
-  DSG_CHECK_ARG(x0 && noise && t && sqrt_ac && sqrt_1mac && out, "dsg_add_noise: null pointer");
   DSG_CHECK_ARG(batch >= 0 && batch <= 65535 && per_sample >= 0, "dsg_add_noise: bad batch/per_sample");
   if (batch == 0 || per_sample == 0) return DSG_OK;
+  DSG_CHECK_ARG(x0 && noise && t && sqrt_ac && sqrt_1mac && out, "dsg_add_noise: null pointer");
   DSG_CHECK_ARG(((uintptr_t)x0 | (uintptr_t)noise | (uintptr_t)out) % 16 == 0,
                 "dsg_add_noise: pointers must be 16-byte aligned");
   dim3 grid(grid_for(per_sample / 4 + 1, 256, 148 * 2), batch);
@@ -168,9 +170,9 @@ int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const f
 
 int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, int32_t n, int32_t c, int32_t h,
                         int32_t w, void* stream) {
-  DSG_CHECK_ARG(latent && (out_u8 || out_f32), "dsg_latent_to_image: null pointer");
   DSG_CHECK_ARG(n >= 0 && c > 0 && h > 0 && w > 0, "dsg_latent_to_image: bad shape");
   if (n == 0) return DSG_OK;
+  DSG_CHECK_ARG(latent && (out_u8 || out_f32), "dsg_latent_to_image: null pointer");
   const int64_t hw = (int64_t)h * w;
   latent_to_image_kernel<<<grid_for(hw * n, 256), 256, 0, (cudaStream_t)stream>>>(latent, out_u8, out_f32, c, hw,
                                                                                  hw * n);

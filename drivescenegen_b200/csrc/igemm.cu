@@ -378,8 +378,8 @@ static IgSrc dense_src(const void* ptr, int C, int H, int W) {
 static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   memset(&p, 0, sizeof(p));
   DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "dsg_conv: bad mode %d", a->mode);
-  DSG_CHECK_ARG(a->x && a->wpacked && a->out, "dsg_conv: null x/wpacked/out");
   DSG_CHECK_ARG(a->n >= 0 && a->h > 0 && a->w > 0, "dsg_conv: bad shape");
+  DSG_CHECK_ARG(a->n == 0 || (a->x && a->wpacked && a->out), "dsg_conv: null x/wpacked/out");
   DSG_CHECK_ARG(a->cin > 0 && a->cin % 64 == 0 && a->cout > 0 && a->cout % 64 == 0,
                 "dsg_conv: cin (%d) and cout (%d) must be multiples of 64", a->cin, a->cout);
   DSG_CHECK_ARG(a->csc1 % 64 == 0 && a->csc2 % 64 == 0 && a->csc1 >= 0 && a->csc2 >= 0,

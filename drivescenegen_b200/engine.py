@@ -243,6 +243,7 @@ class _Program:
         self.eng, self.b, self.h, self.w = eng, batch, h, w
         self.lib = eng.lib
         self.ops: List[Callable[[int], None]] = []
+        self.op_info: List[Tuple[str, dict]] = []
         self.keep: list = []          # ctypes structs / tensors that must outlive the closures
         self.uid = 0
         self.in_ptr = C.c_void_p(0)   # set per run (or to a static buffer under graph capture)
@@ -256,7 +257,7 @@ class _Program:
         for (name, dtype), numel in self._measure.items():
             eng.arena.get(name, numel, dtype)
         self._measure = None
-        self.ops, self.keep = [], []
+        self.ops, self.keep, self.op_info = [], [], []
         self._build()
 
     # --- buffers -------------------------------------------------------------------------------------
@@ -276,6 +277,10 @@ class _Program:
         return self._tmp_raw(name, self.b * hw[0] * hw[1] * ch, torch.float16)
 
     # --- op emitters ---------------------------------------------------------------------------------
+    def _emit(self, name: str, meta: dict, fn: Callable[[int], None]):
+        self.ops.append(fn)
+        self.op_info.append((name, meta))
+
     def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out):
         eng, lib, b = self.eng, self.lib, self.b
         npx = hw[0] * hw[1]
@@ -285,8 +290,9 @@ class _Program:
         a1 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), b, npx, eng.groups)
         a2 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), g.data_ptr(), bt.data_ptr(), eng.eps, act, out.data_ptr(), b,
               npx, eng.groups)
-        self.ops.append(lambda st, a=a1: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
-        self.ops.append(lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
+        nbytes = b * npx * (c1 + c2) * 2
+        self._emit("gn_stats", {"bytes": nbytes}, lambda st, a=a1: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
+        self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
 
     def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
               sc2=None, csc2=0):
@@ -305,7 +311,11 @@ class _Program:
         a.impl = eng.conv_impl
         self.keep.append(a)
         ref = C.byref(a)
-        self.ops.append(lambda st, r=ref: check(lib.dsg_conv(r, st), f"conv {wname}"))
+        k_ref = {0: 9 * cin + csc1 + csc2, 1: 9 * cin, 2: 9 * cin, 3: cin}[mode]
+        opx = {0: hw[0] * hw[1], 1: hw[0] * hw[1] // 4, 2: hw[0] * hw[1] * 4, 3: hw[0] * hw[1]}[mode]
+        meta = {"mode": mode, "hw": hw, "cin": cin + csc1 + csc2, "cout": cout,
+                "flops": 2 * self.b * opx * cout * k_ref}  # algorithmic (reference op count, no sub-pixel discount)
+        self._emit("conv", meta, lambda st, r=ref: check(lib.dsg_conv(r, st), f"conv {wname}"))
 
     def _resnet(self, r, x1, x2, hw, out):
         c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
@@ -329,7 +339,9 @@ class _Program:
         self._conv(3, act, hw, ch, 3 * ch, f"{pre}.qkv", f"{pre}.qkv.b", qkv)
         o = self._tmp("attn_o", hw, ch)
         args = (qkv.data_ptr(), o.data_ptr(), b, hw[0] * hw[1], ch // hd, hd)
-        self.ops.append(lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
+        ntok = hw[0] * hw[1]
+        self._emit("attention", {"flops": 4 * b * ntok * ntok * ch, "exps": b * (ch // hd) * ntok * ntok},
+                   lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
         self._conv(3, o, hw, ch, ch, f"{pre}.out", f"{pre}.out.b", out, residual=x)
 
     # --- whole forward -------------------------------------------------------------------------------
@@ -345,11 +357,12 @@ class _Program:
                    W["te.linear_2.w"].data_ptr(), W["te.linear_2.b"].data_ptr(), eng.temb_hidden,
                    W["te.proj.w"].data_ptr(), W["te.proj.b"].data_ptr(), eng.proj_total, emb_ws.data_ptr(),
                    self.temb.data_ptr(), b)
-        self.ops.append(lambda st: check(lib.dsg_time_embed(self.t_ptr, *te_args, st), "time_embed"))
+        self._emit("time_embed", {}, lambda st: check(lib.dsg_time_embed(self.t_ptr, *te_args, st), "time_embed"))
         c0 = eng.cfg["block_out_channels"][0]
         x = self._new("conv_in", hw, c0)
         ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(), b, self.cin, hw[0], hw[1], c0)
-        self.ops.append(lambda st: check(lib.dsg_conv_in(self.in_ptr, *ci_args, st), "conv_in"))
+        self._emit("conv_in", {"bytes": b * hw[0] * hw[1] * (self.cin * 4 + c0 * 2)},
+                   lambda st: check(lib.dsg_conv_in(self.in_ptr, *ci_args, st), "conv_in"))
         skips = [(x, c0, hw)]
         for i, blk in enumerate(eng.down):
             for j, r in enumerate(blk["resnets"]):
@@ -403,8 +416,30 @@ class _Program:
         self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
         co_args = (act.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
         co_tail = (b, c0, hw[0], hw[1], self.cout)
-        self.ops.append(lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
+        self._emit("conv_out", {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2)},
+                   lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
         self.n_launches = len(self.ops) + 1  # time_embed is two launches
+
+    def run_timed(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """Eager replay with a CUDA-event pair around every launch; returns [(name, meta, milliseconds)]."""
+        dev = sample.device
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        ops = self.ops
+        hooked = []
+        stream = torch.cuda.current_stream(dev)
+        for i, op in enumerate(ops):
+            def h(st, op=op, i=i):
+                op(st)
+                evs[i + 1].record(stream)
+            hooked.append(h)
+        self.ops = hooked
+        try:
+            evs[0].record(stream)
+            self.run(sample, t_float, out)
+        finally:
+            self.ops = ops
+        torch.cuda.synchronize(dev)
+        return [(n, m, evs[i].elapsed_time(evs[i + 1])) for i, (n, m) in enumerate(self.op_info)]
 
     def run(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if sample.dtype != torch.float32 or not sample.is_contiguous():

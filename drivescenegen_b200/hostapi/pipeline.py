@@ -48,10 +48,15 @@ def numpy_to_pil(images: np.ndarray):
 _SCHEDULERS = {"DDPMScheduler": DDPMScheduler, "DDIMScheduler": DDIMScheduler}
 
 
-class _GraphedStep:
-    """One captured CUDA graph = U-Net forward + scheduler step on static buffers."""
+class DenoiseSession:
+    """One captured CUDA graph = U-Net forward + scheduler step on static device buffers.
 
-    def __init__(self, unet: UNet2DModel, scheduler, shape, ddim: bool, eta: float):
+    ``x`` holds the current sample; ``step(t)`` advances it by one denoising step.  ``step_from_host`` is the
+    end-to-end form: the step's variance noise comes from (pinned) host memory and the new sample is copied back
+    to (pinned) host memory, both inside the call.
+    """
+
+    def __init__(self, unet: UNet2DModel, scheduler, shape, ddim: bool = False, eta: float = 0.0):
         self.lib = _lib.load()
         dev = unet.device
         self.dev = dev
@@ -87,6 +92,19 @@ class _GraphedStep:
     def set_step(self, t: int):
         self.t_f.fill_(float(t))
         self.row.fill_(int(t))
+
+    def step(self, t: int, noise: Optional[torch.Tensor] = None):
+        self.set_step(t)
+        if noise is not None:
+            self.z.copy_(noise, non_blocking=True)
+        self.graph.replay()
+        return self.x
+
+    def step_from_host(self, t: int, noise_host: torch.Tensor, out_host: torch.Tensor):
+        self.step(t, noise_host)
+        out_host.copy_(self.x, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return out_host
 
 
 class DDPMPipeline:
@@ -175,7 +193,7 @@ class DDPMPipeline:
             gs = self._graph_cache.get(key)
             if gs is None:
                 self._graph_cache.clear()
-                gs = _GraphedStep(self.unet, sched, tuple(image.shape), ddim, eta)
+                gs = DenoiseSession(self.unet, sched, tuple(image.shape), ddim, eta)
                 self._graph_cache[key] = gs
             gs.x.copy_(image)
             for t in self.progress_bar(sched.timesteps):
