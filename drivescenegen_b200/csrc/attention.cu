@@ -7,12 +7,14 @@
 namespace dsg {
 
 constexpr int AT_THREADS = 128;
-constexpr int AT_KTILE = 512;  // keys staged per smem tile
+// keys staged per smem tile (fp32 K and V): 2 * KTILE * D * 4 bytes <= 128 KB
+template <int D> struct AtTile { static constexpr int K = D <= 32 ? 512 : 256; };
 
 template <int D>
 __global__ void __launch_bounds__(AT_THREADS) attention_kernel(const __half* __restrict__ qkv,
                                                                __half* __restrict__ out, int tokens, int heads,
                                                                float scale_log2e) {
+  constexpr int AT_KTILE = AtTile<D>::K;
   extern __shared__ float smf[];
   float* sk = smf;                 // [AT_KTILE][D]
   float* sv = smf + AT_KTILE * D;  // [AT_KTILE][D]
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_kernel(const __half* __r
 
 template <int D>
 static int launch_attention(const __half* qkv, __half* out, int n, int tokens, int heads, cudaStream_t st) {
-  const size_t sm = (size_t)2 * AT_KTILE * D * sizeof(float);
+  const size_t sm = (size_t)2 * AtTile<D>::K * D * sizeof(float);
   if (sm > 48 * 1024)
     cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
