@@ -8,6 +8,7 @@ namespace dsg {
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_ILP = 4;
 
 __device__ __forceinline__ const __half* src_of(const __half* x1, int c1, const __half* x2, int c2, int64_t pix,
                                                 int ch) {
@@ -41,15 +42,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
     const int64_t p_begin = (int64_t)chunk * px_per_chunk;
     int64_t p_end = p_begin + px_per_chunk;
     if (p_end > hw) p_end = hw;
-    for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
-      uint4 raw = ldg_nc_v4(src + (base_px + p) * cs + co);
-      float f[8];
-      unpack8(raw, f);
+    // GN_ILP independent 16-byte loads in flight per thread: the loop is latency-bound otherwise
+    for (int64_t p = p_begin + prow; p < p_end; p += (int64_t)ppi * GN_ILP) {
+      uint4 raw[GN_ILP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[j] - K[j];
-        s[j] += d;
-        q[j] = fmaf(d, d, q[j]);
+      for (int u = 0; u < GN_ILP; ++u) {
+        const int64_t pp = p + (int64_t)u * ppi;
+        if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+      }
+#pragma unroll
+      for (int u = 0; u < GN_ILP; ++u) {
+        if (p + (int64_t)u * ppi < p_end) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - K[j];
+            s[j] += d;
+            q[j] = fmaf(d, d, q[j]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -118,16 +130,27 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   const int64_t p_begin = (int64_t)blockIdx.x * px_per_cta;
   int64_t p_end = p_begin + px_per_cta;
   if (p_end > hw) p_end = hw;
-  for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
-    uint4 raw = ldg_nc_v4(src + (base_px + p) * cs + co);
-    float f[8];
-    unpack8(raw, f);
+  for (int64_t p = p_begin + prow; p < p_end; p += (int64_t)ppi * GN_ILP) {
+    uint4 raw[GN_ILP];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(f[j], a[j], b[j]);
-      f[j] = act ? silu_f(t) : t;
+    for (int u = 0; u < GN_ILP; ++u) {
+      const int64_t pp = p + (int64_t)u * ppi;
+      if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
     }
-    stg_v4(y + (base_px + p) * C + ch0, pack8(f));
+#pragma unroll
+    for (int u = 0; u < GN_ILP; ++u) {
+      const int64_t pp = p + (int64_t)u * ppi;
+      if (pp < p_end) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(f[j], a[j], b[j]);
+          f[j] = act ? silu_f(t) : t;
+        }
+        stg_v4(y + (base_px + pp) * C + ch0, pack8(f));
+      }
+    }
   }
 }
 

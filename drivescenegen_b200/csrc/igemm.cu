@@ -11,22 +11,14 @@
 // (M=128, N=BLOCK_N, K=16, fp16 in / fp32 accumulate in TMEM).  Persistent, warp-specialised:
 //   warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> regs -> +bias/temb/residual -> fp16).
 // TMEM accumulators are double-buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-#include "common.cuh"
+#include "igemm_common.cuh"
 
 namespace dsg {
 
-constexpr int IG_BLOCK_M = 128;
-constexpr int IG_BLOCK_K = 64;
 constexpr int IG_THREADS = 192;
-constexpr int IG_MAX_SRC = 4;
 constexpr int IG_MAX_TAPS = 12;
 constexpr int IG_A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 2;  // 16 KB
 
-struct IgSrc {
-  const __half* ptr;
-  int64_t sN, sH, sW;  // element strides
-  int C, H, W;         // logical extents (out-of-range reads are zero)
-};
 struct IgTap {
   int src, dy, dx, nchunks;
 };
@@ -304,77 +296,6 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float*
   }
 }
 
-// ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)f;
-  }
-  return fn;
-}
-
-static int make_map_a(CUtensorMap* m, const IgSrc& s, int N, int TW, int box_h) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DSG_ERR_CUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)s.sW * 2, (cuuint64_t)s.sH * 2, (cuuint64_t)s.sN * 2};
-  cuuint32_t box[4] = {(cuuint32_t)IG_BLOCK_K, (cuuint32_t)TW, (cuuint32_t)box_h, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)s.ptr, dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(A) failed: %d (C=%d W=%d H=%d N=%d TW=%d TH=%d)", (int)r, s.C, s.W, s.H, N, TW,
-              box_h);
-    return DSG_ERR_CUDA;
-  }
-  return DSG_OK;
-}
-
-static int make_map_b(CUtensorMap* m, const __half* w, int64_t k_total, int64_t rows, int block_n) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DSG_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-  cuuint32_t box[2] = {(cuuint32_t)IG_BLOCK_K, (cuuint32_t)block_n};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)w, dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(B) failed: %d (K=%lld rows=%lld bn=%d)", (int)r, (long long)k_total,
-              (long long)rows, block_n);
-    return DSG_ERR_CUDA;
-  }
-  return DSG_OK;
-}
-
-static int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
-
-static IgSrc dense_src(const void* ptr, int C, int H, int W) {
-  IgSrc s;
-  s.ptr = (const __half*)ptr; s.C = C; s.H = H; s.W = W;
-  s.sW = C; s.sH = (int64_t)W * C; s.sN = (int64_t)H * W * C;
-  return s;
-}
-
 static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   memset(&p, 0, sizeof(p));
   DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "dsg_conv: bad mode %d", a->mode);
@@ -525,11 +446,16 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
     DSG_CUDA_LAUNCH_CHECK("dsg_conv/naive");
     return DSG_OK;
   }
-  DSG_CHECK_ARG(a->impl == 0, "dsg_conv: bad impl %d", a->impl);
+  DSG_CHECK_ARG(a->impl == 0 || a->impl == 2 || a->impl == 3, "dsg_conv: bad impl %d", a->impl);
   int bn = a->block_n;
   if (bn == 0) bn = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
   DSG_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && a->cout % bn == 0, "dsg_conv: bad block_n %d for cout %d", bn,
                 a->cout);
+  if (a->impl != 2) {
+    rc = launch_halo_conv(a, bn, st);
+    if (rc != DSG_HALO_SKIP) return rc;
+    if (a->impl == 3) { set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel"); return DSG_ERR_UNSUPPORTED; }
+  }
   switch (bn) {
     case 64: return launch_igemm<64>(p, st);
     case 128: return launch_igemm<128>(p, st);

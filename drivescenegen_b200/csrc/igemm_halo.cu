@@ -1,0 +1,383 @@
+// igemm_halo.cu — halo-reuse implicit-GEMM convolution on tcgen05 tensor cores (3x3 stride-1 and the sub-pixel
+// form of nearest-2x-upsample + 3x3).  Same contraction and packed weights as igemm.cu (the tap-streaming kernel),
+// but the activation tile is fetched ONCE per column shift instead of once per tap:
+//
+//   CTA tile = TH x TW output pixels (TW = 16 or 8, TH = MT * 128 / TW), i.e. MT stacked M = 128 accumulators.
+//   For each 64-channel chunk and each dx in {-1, 0, +1} one TMA box of (TH + 2) rows x TW pixels x 64 channels
+//   lands in a 128B-swizzled smem slot.  Box rows are TW * 128 B = a multiple of the 1024 B swizzle atom, so the
+//   A operand of tap (dy, dx) for accumulator m is simply the SAME slot at byte offset (dy + 1 + m * 128 / TW) *
+//   TW * 128 — a descriptor start-address bump, no data movement.  Out-of-bounds rows/columns are zero-filled by
+//   the TMA unit, which is the conv zero padding.  Weights stream through a second, finer ring (one BLOCK_N x 64
+//   tile per tap).  L2 -> smem traffic per 64-channel chunk drops from 9 x 16 KB per 128 pixels to
+//   3 x (TH + 2) / TH x 16 KB, and every weight tile is reused by MT accumulators.
+//
+// Warp roles as in igemm.cu: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> +bias/temb/residual -> fp16 NHWC).  TMEM holds 2 x MT accumulators (double-buffered).
+// Replaces the cuDNN convs behind ResnetBlock2D.conv1/conv2(+conv_shortcut) and Upsample2D of diffusers 0.20.0
+// (SURVEY.md §2.2, §8 a4/a6).
+#include "igemm_common.cuh"
+
+namespace dsg {
+
+constexpr int HL_THREADS = 192;
+constexpr int HL_MAX_GROUPS = 5;
+constexpr int HL_MAX_MAPS = 3;
+
+struct HlGroup {
+  int map;         // which activation tensor map (source + box height)
+  int dx, dy0;     // box origin relative to the tile origin (phase offset added at run time)
+  int nchunks;     // 64-channel chunks of this source
+  int ntaps;       // taps served by one box (<= 3)
+  int row_off[3];  // first box row of tap t
+  int kb_base[3];  // weight k-block (64 columns each) of (tap t, chunk 0)
+  int bytes;       // bytes one box delivers
+};
+
+struct HlPlan {
+  HlGroup grp[HL_MAX_GROUPS];
+  int ngroups;
+  int N, OH, OW;
+  int TW, tw_shift, TH;  // CTA tile = TH x TW pixels
+  int tiles_w, tiles_h;
+  int phases, omul;
+  int cout, n_blocks;
+  int64_t oN, oH, oW;  // output element strides
+  __half* out;
+  const __half* res;
+  const float* bias;
+  const float* temb;
+  int temb_stride, temb_off;
+  int64_t total_tiles;
+};
+
+struct alignas(64) HlMaps {
+  CUtensorMap a[HL_MAX_MAPS];
+  CUtensorMap b;
+};
+
+template <int BLOCK_N, int MT>
+struct HlCfg {
+  static constexpr int A_SLOT = MT * 16384 + 4096;  // (MT*8 + 2) rows x 16 px x 128 B (the TW = 8 box is smaller)
+  static constexpr int B_SLOT = BLOCK_N * 128;
+  static constexpr int NA = BLOCK_N == 64 ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int NB = BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4);
+  static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
+  static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
+  static constexpr int SMEM_BYTES = RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
+  static_assert(TMEM_COLS <= 512, "TMEM overflow");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
+};
+
+struct HlTile {
+  int n, h0, w0, nb, pa, pb;
+};
+__device__ __forceinline__ HlTile hl_decode(const HlPlan& p, int64_t t) {
+  HlTile c;
+  c.nb = (int)(t % p.n_blocks); t /= p.n_blocks;
+  const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
+  const int th = (int)(t % p.tiles_h); t /= p.tiles_h;
+  c.n = (int)(t % p.N);
+  const int phase = (int)(t / p.N);
+  c.pa = phase >> 1; c.pb = phase & 1;
+  c.h0 = th * p.TH; c.w0 = tw * p.TW;
+  return c;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int BLOCK_N, int MT>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ HlPlan p) {
+  using Cfg = HlCfg<BLOCK_N, MT>;
+  constexpr int NA = Cfg::NA, NB = Cfg::NB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + NA * Cfg::A_SLOT;
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);  // [2][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 2 * BLOCK_N);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* b_full = a_empty + NA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* tfull = b_empty + NB;   // [2]
+  uint64_t* tempty = tfull + 2;     // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half_rows = 128 >> p.tw_shift;  // image rows per M = 128 accumulator
+  const int row_bytes = p.TW * 128;         // one box row in smem
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < HL_MAX_MAPS; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (one lane)
+    if (lane == 0) {
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const HlTile tc = hl_decode(p, t);
+        const int brow = (tc.pa * 2 + tc.pb) * p.cout + tc.nb * BLOCK_N;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const HlGroup& G = p.grp[g];
+          const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
+          for (int c = 0; c < G.nchunks; ++c) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_arrive_expect_tx(&a_full[as], (uint32_t)G.bytes);
+            tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_full[as], c * IG_BLOCK_K, wx, hy, tc.n);
+            if (++as == NA) { as = 0; aph ^= 1; }
+            for (int tp = 0; tp < G.ntaps; ++tp) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
+              tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+              if (++bs == NB) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(BLOCK_N);
+      int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
+      int acc = 0; uint32_t acc_ph = 0;
+      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BLOCK_N);
+        uint32_t accum = 0;  // the first k-step of the first tap initialises every accumulator
+        for (int g = 0; g < p.ngroups; ++g) {
+          const HlGroup& G = p.grp[g];
+          for (int c = 0; c < G.nchunks; ++c) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_ring + as * Cfg::A_SLOT);
+            for (int tp = 0; tp < G.ntaps; ++tp) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bs * Cfg::B_SLOT));
+#pragma unroll
+              for (int m = 0; m < MT; ++m) {
+                const uint64_t da = umma_desc_sw128(a_addr + (uint32_t)((G.row_off[tp] + m * half_rows) * row_bytes));
+#pragma unroll
+                for (int k = 0; k < IG_BLOCK_K / 16; ++k)
+                  umma_f16(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                           k == 0 ? accum : 1u);
+              }
+              accum = 1;
+              umma_commit(&b_empty[bs]);  // frees the weight slot when these MMAs retire
+              if (++bs == NB) { bs = 0; bph ^= 1; }
+            }
+            umma_commit(&a_empty[as]);    // frees the activation box
+            if (++as == NA) { as = 0; aph ^= 1; }
+          }
+        }
+        umma_commit(&tfull[acc]);         // accumulators complete -> epilogue
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int te = threadIdx.x - 64;
+    const int lh0 = row >> p.tw_shift, lw = row & (p.TW - 1);
+    constexpr int NCH = BLOCK_N / 32;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const HlTile tc = hl_decode(p, t);
+      const int n0 = tc.nb * BLOCK_N;
+      float* sb = sbias + acc * BLOCK_N;
+      for (int j = te; j < BLOCK_N; j += 128) {
+        float v = p.bias ? p.bias[n0 + j] : 0.f;
+        if (p.temb) v += p.temb[(int64_t)tc.n * p.temb_stride + p.temb_off + n0 + j];
+        sb[j] = v;
+      }
+      int64_t off[MT];
+      bool valid[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int h = tc.h0 + m * half_rows + lh0, w = tc.w0 + lw;
+        valid[m] = (h < p.OH) && (w < p.OW);
+        off[m] = (int64_t)tc.n * p.oN + (int64_t)(h * p.omul + tc.pa) * p.oH + (int64_t)(w * p.omul + tc.pb) * p.oW + n0;
+        if (p.res && valid[m]) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N; j += 64) prefetch_l2(p.res + off[m] + j);
+        }
+      }
+      uint4 rnext[4];
+      if (p.res && valid[0]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = ldg_nc_v4(p.res + off[0] + j * 8);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * MT * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(m * BLOCK_N + c * 32), v);
+          uint4 rcur[4];
+          if (p.res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+            // prefetch the next 32-column slice of the residual (next chunk, or chunk 0 of the next accumulator)
+            const int nm = (c + 1 < NCH) ? m : m + 1, nc = (c + 1 < NCH) ? c + 1 : 0;
+            if (nm < MT && valid[nm < MT ? nm : 0]) {
+              const __half* rp = p.res + off[nm < MT ? nm : 0] + nc * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rnext[j] = ldg_nc_v4(rp + j * 8);
+            }
+          }
+          tmem_ld_wait();
+          if (valid[m]) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+              f[j] = __uint_as_float(v[j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (p.res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float r[8];
+                unpack8(rcur[j], r);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[j * 8 + u] += r[u];
+              }
+            }
+            __half* op = p.out + off[m] + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1; if (acc == 0) acc_ph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+template <int BLOCK_N, int MT>
+static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
+  using Cfg = HlCfg<BLOCK_N, MT>;
+  HlPlan p;
+  memset(&p, 0, sizeof(p));
+  const int oh = a->h, ow = a->w;  // GEMM pixel grid (per phase for mode 2)
+  int tw, sh;
+  if (ow >= 16) { tw = 16; sh = 4; } else if (ow >= 8) { tw = 8; sh = 3; } else return DSG_HALO_SKIP;
+  const int th = MT * (128 / tw);
+  const int halo = a->mode == 0 ? 2 : 1;
+  if (oh < th + halo) return DSG_HALO_SKIP;  // keep every TMA box inside the tensor extents
+  p.N = a->n; p.OH = oh; p.OW = ow; p.TW = tw; p.tw_shift = sh; p.TH = th;
+  p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th);
+  p.cout = a->cout; p.n_blocks = a->cout / BLOCK_N;
+  const int cin_chunks = a->cin / 64;
+  HlMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  IgSrc src0 = dense_src(a->x, a->cin, a->h, a->w);
+  int rc = make_map_a(&maps.a[0], src0, a->n, tw, th + halo);
+  if (rc) return rc;
+  int64_t k_total;
+  if (a->mode == 0) {
+    p.phases = 1; p.omul = 1;
+    for (int dx = -1; dx <= 1; ++dx) {
+      HlGroup& G = p.grp[p.ngroups++];
+      G.map = 0; G.dx = dx; G.dy0 = -1; G.nchunks = cin_chunks; G.ntaps = 3;
+      for (int dy = -1; dy <= 1; ++dy) {
+        G.row_off[dy + 1] = dy + 1;
+        G.kb_base[dy + 1] = ((dy + 1) * 3 + (dx + 1)) * cin_chunks;
+      }
+      G.bytes = (th + 2) * tw * 128;
+    }
+    int kb = 9 * cin_chunks;
+    const void* scp[2] = {a->sc1, a->sc2};
+    const int scc[2] = {a->csc1, a->csc2};
+    for (int s = 0; s < 2; ++s) {
+      if (!scc[s]) continue;
+      IgSrc ss = dense_src(scp[s], scc[s], a->h, a->w);
+      rc = make_map_a(&maps.a[1 + s], ss, a->n, tw, th);
+      if (rc) return rc;
+      HlGroup& G = p.grp[p.ngroups++];
+      G.map = 1 + s; G.dx = 0; G.dy0 = 0; G.nchunks = scc[s] / 64; G.ntaps = 1;
+      G.row_off[0] = 0; G.kb_base[0] = kb;
+      G.bytes = th * tw * 128;
+      kb += scc[s] / 64;
+    }
+    k_total = (int64_t)kb * 64;
+  } else {  // mode 2: four sub-pixel phases, each a 2x2 conv at the input resolution
+    p.phases = 4; p.omul = 2;
+    for (int j = 0; j < 2; ++j) {
+      HlGroup& G = p.grp[p.ngroups++];
+      G.map = 0; G.dx = j - 1; G.dy0 = -1; G.nchunks = cin_chunks; G.ntaps = 2;
+      for (int i = 0; i < 2; ++i) {
+        G.row_off[i] = i;
+        G.kb_base[i] = (i * 2 + j) * cin_chunks;
+      }
+      G.bytes = (th + 1) * tw * 128;
+    }
+    k_total = (int64_t)4 * a->cin;
+  }
+  rc = make_map_b(&maps.b, (const __half*)a->wpacked, k_total, (int64_t)p.phases * a->cout, BLOCK_N);
+  if (rc) return rc;
+  const int out_h = oh * p.omul, out_w = ow * p.omul;
+  p.oW = a->cout; p.oH = (int64_t)out_w * a->cout; p.oN = (int64_t)out_h * out_w * a->cout;
+  p.out = (__half*)a->out; p.res = (const __half*)a->residual;
+  p.bias = a->bias; p.temb = a->temb; p.temb_stride = a->temb_stride; p.temb_off = a->temb_off;
+  p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("igemm_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  igemm_halo_kernel<BLOCK_N, MT><<<(unsigned)grid, HL_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  DSG_CUDA_LAUNCH_CHECK("dsg_conv/igemm_halo");
+  return DSG_OK;
+}
+
+int launch_halo_conv(const dsg_conv_args* a, int block_n, cudaStream_t st) {
+  if (a->mode != 0 && a->mode != 2) return DSG_HALO_SKIP;
+  switch (block_n) {
+    case 64: return launch_halo<64, 2>(a, st);
+    case 128: return launch_halo<128, 2>(a, st);
+    case 256: return launch_halo<256, 1>(a, st);
+    default: return DSG_HALO_SKIP;
+  }
+}
+
+}  // namespace dsg

@@ -109,7 +109,10 @@ typedef struct dsg_conv_args {
   const void* residual;
   void* out;
   int32_t block_n; /* 0 = auto, else 64/128/256 */
-  int32_t impl;    /* 0 = tcgen05 path, 1 = plain CUDA-core cross-check kernel (slow; debugging/tests only) */
+  int32_t impl;    /* 0 = tcgen05 path (halo-reuse kernel where it applies, else the tap-streaming kernel),
+                      1 = plain CUDA-core cross-check kernel (slow; debugging/tests only),
+                      2 = force the tap-streaming tcgen05 kernel, 3 = force the halo-reuse tcgen05 kernel
+                      (DSG_ERR_UNSUPPORTED when the mode/shape is outside it: modes 0 and 2, W >= 8, H >= tile) */
 } dsg_conv_args;
 int dsg_conv(const dsg_conv_args* args, void* stream);
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */

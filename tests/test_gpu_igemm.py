@@ -85,15 +85,89 @@ def test_igemm_conv(case):
     torch.cuda.synchronize()
     err_naive = (naive.float().permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
     assert err_naive < 2e-2, f"cross-check kernel vs torch: {err_naive}"
-    fast = ops.conv(mode, x.to(d), wp, cout, impl=0, block_n=block_n, **kw)
+    # impl 0 = auto (halo-reuse kernel where it applies), impl 2 = tap-streaming kernel forced
+    for impl in (0, 2):
+        fast = ops.conv(mode, x.to(d), wp, cout, impl=impl, block_n=block_n, **kw)
+        torch.cuda.synchronize()
+        diff = (fast.float() - naive.float()).abs().max().item()
+        err = (fast.float().permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
+        # both kernels round the same fp32 sums (different accumulation order) to fp16: at most ~1 fp16 ulp apart,
+        # 1 ulp = 2^-10 relative to the output magnitude
+        scale = max(1.0, ref.abs().max().item())
+        assert diff <= 2.0 ** -9 * scale, f"tcgen05 (impl {impl}) vs cross-check kernel: {diff} (scale {scale})"
+        assert err < 2e-2, f"tcgen05 (impl {impl}) vs torch fp32: {err}"
+
+
+# shapes the halo-reuse kernel must cover itself (impl = 3 raises instead of falling back)
+HALO_CASES = [
+    # mode, n, h, w, cin, cout, csc1, csc2, residual, temb, block_n
+    (0, 2, 32, 32, 64, 64, 0, 0, True, True, 0),        # BLOCK_N 64, two stacked accumulators (16x16 tiles)
+    (0, 1, 40, 24, 64, 64, 0, 0, True, False, 0),       # ragged: H, W not multiples of the tile
+    (0, 2, 24, 16, 128, 128, 0, 0, False, True, 0),     # BLOCK_N 128, second accumulator half outside the image
+    (0, 1, 32, 8, 64, 128, 0, 0, True, False, 0),       # TW = 8 tiles (32 rows tall)
+    (0, 2, 16, 16, 128, 256, 0, 0, True, True, 0),      # BLOCK_N 256, one accumulator
+    (0, 3, 32, 32, 512, 512, 0, 0, True, True, 0),      # long K loop, two N blocks
+    (0, 1, 32, 32, 64, 128, 64, 128, False, False, 0),  # fused 1x1 shortcut over two sources
+    (0, 1, 64, 64, 192, 64, 128, 64, False, True, 0),   # up-block conv2 shape: shortcut panels + temb
+    (0, 1, 256, 256, 64, 64, 0, 0, True, False, 0),     # many tiles per CTA (persistent loop, ring wrap-around)
+    (2, 2, 16, 16, 64, 64, 0, 0, False, False, 0),      # H below the two-accumulator tile + halo: skipped (impl 3 refuses)
+    (2, 1, 32, 32, 128, 128, 0, 0, False, False, 0),
+    (2, 1, 32, 32, 256, 256, 0, 0, False, False, 0),
+    (2, 2, 32, 48, 64, 64, 0, 0, False, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[str(c) for c in HALO_CASES])
+def test_igemm_halo_kernel(case):
+    from drivescenegen_b200 import ops
+    from drivescenegen_b200._lib import DsgError
+    mode, n, h, w, cin, cout, csc1, csc2, use_res, use_temb, block_n = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    d = _dev()
+    x = torch.randn(n, h, w, cin, generator=g).half()
+    fan = cin * 9 + csc1 + csc2
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / fan ** 0.5
+    b = torch.randn(cout, generator=g)
+    oh, ow = (2 * h, 2 * w) if mode == 2 else (h, w)
+    sc = []
+    if csc1:
+        sc.append(torch.randn(n, h, w, csc1, generator=g).half())
+    if csc2:
+        sc.append(torch.randn(n, h, w, csc2, generator=g).half())
+    w_sc = torch.randn(cout, csc1 + csc2, generator=g) / fan ** 0.5 if sc else None
+    res = torch.randn(n, oh, ow, cout, generator=g).half() if use_res else None
+    temb = torch.randn(n, cout + 32, generator=g) if use_temb else None
+    ref = _ref_conv(mode, x, wt, b, temb, 32 if use_temb else 0, res, sc, w_sc)
+    wp = ops.pack_conv_weight(mode, wt.to(d), None if w_sc is None else w_sc.to(d))
+    kw = dict(bias=b.to(d), temb=None if temb is None else temb.to(d), temb_off=32 if use_temb else 0,
+              residual=None if res is None else res.to(d), sc1=sc[0].to(d) if len(sc) > 0 else None,
+              sc2=sc[1].to(d) if len(sc) > 1 else None)
+    naive = ops.conv(mode, x.to(d), wp, cout, impl=1, **kw)
+    try:
+        fast = ops.conv(mode, x.to(d), wp, cout, impl=3, block_n=block_n, **kw)
+    except DsgError as e:
+        if "not covered" in str(e) and mode == 2 and h < 17:
+            pytest.skip("shape below the halo kernel's minimum height for this BLOCK_N")
+        raise
     torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
     diff = (fast.float() - naive.float()).abs().max().item()
     err = (fast.float().permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
-    # both kernels round the same fp32 sums (different accumulation order) to fp16: at most ~1 fp16 ulp apart,
-    # 1 ulp = 2^-10 relative to the output magnitude
-    scale = max(1.0, ref.abs().max().item())
-    assert diff <= 2.0 ** -9 * scale, f"tcgen05 vs cross-check kernel: {diff} (scale {scale})"
-    assert err < 2e-2, f"tcgen05 vs torch fp32: {err}"
+    assert diff <= 2.0 ** -9 * scale, f"halo kernel vs cross-check kernel: {diff} (scale {scale})"
+    assert err < 2e-2, f"halo kernel vs torch fp32: {err}"
+
+
+def test_igemm_halo_rejects_uncovered_shapes():
+    from drivescenegen_b200 import ops
+    from drivescenegen_b200._lib import DsgError
+    d = _dev()
+    x = torch.zeros(1, 8, 4, 64, dtype=torch.float16, device=d)   # W < 8
+    wp = torch.zeros(64, 9 * 64, dtype=torch.float16, device=d)
+    with pytest.raises(DsgError):
+        ops.conv(0, x, wp, 64, impl=3)
+    x = torch.zeros(1, 16, 16, 64, dtype=torch.float16, device=d)  # stride-2 is served by the streaming kernel
+    with pytest.raises(DsgError):
+        ops.conv(1, x, wp, 64, impl=3)
 
 
 def test_igemm_rejects_bad_args():
