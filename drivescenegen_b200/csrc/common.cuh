@@ -135,6 +135,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// One elected lane of a fully converged warp.  Warp-specialised roles run WARP-UNIFORM (all 32 lanes execute the
+// loop with identical values) and only the TMA / tcgen05 instructions sit under this predicate: operands computed in
+// uniform control flow live in uniform registers, so UTMALDG / UTCHMMA issue back to back.  Computing them under an
+// `if (lane == 0)` branch instead makes every operand "divergent" and each instruction gets wrapped in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100+ cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -88,7 +88,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -103,11 +104,12 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
 
+  // Roles run warp-uniform; only the TMA / tcgen05 instructions are under elect_one_sync() (see common.cuh).
   if (warp == 0) {
-    // ===================================================== TMA producer (one lane)
-    if (lane == 0) {
+    // ===================================================== TMA producer
+    {
       int stage = 0; uint32_t ph = 0;
       for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
@@ -119,17 +121,20 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
           for (int ch = 0; ch < tp.nchunks; ++ch, ++kb) {
             mbar_wait(&empty_bar[stage], ph ^ 1);
             uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + Cfg::B_BYTES));
-            tma_load_4d(sa, &maps.a[tp.src], &full_bar[stage], ch * IG_BLOCK_K, wx, hy, tc.n);
-            tma_load_2d(sa + IG_A_BYTES, &maps.b, &full_bar[stage], kb * IG_BLOCK_K, brow);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.a_bytes + Cfg::B_BYTES));
+              tma_load_4d(sa, &maps.a[tp.src], &full_bar[stage], ch * IG_BLOCK_K, wx, hy, tc.n);
+              tma_load_2d(sa + IG_A_BYTES, &maps.b, &full_bar[stage], kb * IG_BLOCK_K, brow);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // ===================================================== MMA issuer
+    {
       const uint32_t idesc = umma_idesc_f16(BLOCK_N);
       int stage = 0; uint32_t ph = 0;
       int acc = 0; uint32_t acc_ph = 0;
@@ -142,13 +147,16 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + IG_A_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < IG_BLOCK_K / 16; ++k)
-            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            for (int k = 0; k < IG_BLOCK_K / 16; ++k)
+              umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (kb + 1 == p.num_kb) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }

@@ -106,7 +106,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   uint64_t* tempty = tfull + 2;     // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int half_rows = 128 >> p.tw_shift;  // image rows per M = 128 accumulator
   const int row_bytes = p.TW * 128;         // one box row in smem
 
@@ -124,11 +125,11 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
 
   if (warp == 0) {
-    // ===================================================== TMA producer (one lane)
-    if (lane == 0) {
+    // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
+    {
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HlTile tc = hl_decode(p, t);
@@ -138,13 +139,19 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
           const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
           for (int c = 0; c < G.nchunks; ++c) {
             mbar_wait(&a_empty[as], aph ^ 1);
-            mbar_arrive_expect_tx(&a_full[as], (uint32_t)G.bytes);
-            tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_full[as], c * IG_BLOCK_K, wx, hy, tc.n);
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&a_full[as], (uint32_t)G.bytes);
+              tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_full[as], c * IG_BLOCK_K, wx, hy, tc.n);
+            }
+            __syncwarp();
             if (++as == NA) { as = 0; aph ^= 1; }
             for (int tp = 0; tp < G.ntaps; ++tp) {
               mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
-              tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
+                tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+              }
+              __syncwarp();
               if (++bs == NB) { bs = 0; bph ^= 1; }
             }
           }
@@ -152,8 +159,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp-uniform loop, elected lane issues)
+    {
       const uint32_t idesc = umma_idesc_f16(BLOCK_N);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       int acc = 0; uint32_t acc_ph = 0;
@@ -172,23 +179,28 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
               mbar_wait(&b_full[bs], bph);
               tc_fence_after();
               const uint64_t db = umma_desc_sw128(smem_u32(b_ring + bs * Cfg::B_SLOT));
+              const bool last_tap = (tp + 1 == G.ntaps);
+              const bool last_of_tile = last_tap && (c + 1 == G.nchunks) && (g + 1 == p.ngroups);
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int m = 0; m < MT; ++m) {
-                const uint64_t da = umma_desc_sw128(a_addr + (uint32_t)((G.row_off[tp] + m * half_rows) * row_bytes));
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t da = umma_desc_sw128(a_addr + (uint32_t)((G.row_off[tp] + m * half_rows) * row_bytes));
 #pragma unroll
-                for (int k = 0; k < IG_BLOCK_K / 16; ++k)
-                  umma_f16(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                           k == 0 ? accum : 1u);
+                  for (int k = 0; k < IG_BLOCK_K / 16; ++k)
+                    umma_f16(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                             k == 0 ? accum : 1u);
+                }
+                umma_commit(&b_empty[bs]);                 // frees the weight slot when these MMAs retire
+                if (last_tap) umma_commit(&a_empty[as]);   // frees the activation box
+                if (last_of_tile) umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
               }
+              __syncwarp();
               accum = 1;
-              umma_commit(&b_empty[bs]);  // frees the weight slot when these MMAs retire
               if (++bs == NB) { bs = 0; bph ^= 1; }
             }
-            umma_commit(&a_empty[as]);    // frees the activation box
             if (++as == NA) { as = 0; aph ^= 1; }
           }
         }
-        umma_commit(&tfull[acc]);         // accumulators complete -> epilogue
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }

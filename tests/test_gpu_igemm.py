@@ -104,7 +104,7 @@ HALO_CASES = [
     (0, 2, 32, 32, 64, 64, 0, 0, True, True, 0),        # BLOCK_N 64, two stacked accumulators (16x16 tiles)
     (0, 1, 40, 24, 64, 64, 0, 0, True, False, 0),       # ragged: H, W not multiples of the tile
     (0, 2, 24, 16, 128, 128, 0, 0, False, True, 0),     # BLOCK_N 128, second accumulator half outside the image
-    (0, 1, 32, 8, 64, 128, 0, 0, True, False, 0),       # TW = 8 tiles (32 rows tall)
+    (0, 1, 40, 8, 64, 128, 0, 0, True, False, 0),       # TW = 8 tiles (32 rows tall)
     (0, 2, 16, 16, 128, 256, 0, 0, True, True, 0),      # BLOCK_N 256, one accumulator
     (0, 3, 32, 32, 512, 512, 0, 0, True, True, 0),      # long K loop, two N blocks
     (0, 1, 32, 32, 64, 128, 64, 128, False, False, 0),  # fused 1x1 shortcut over two sources

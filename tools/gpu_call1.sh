@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_run.log 2>&1
 for n in 64 128 256; do
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k "regex:igemm_halo_kernel<${n}" -s 12 -c 2 -o gpurun_out/prof_halo${n} \
+      -k "regex:igemm_halo_kernel<\\(int\\)${n}," -s 12 -c 2 -o gpurun_out/prof_halo${n} \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_halo${n}.log 2>&1
 done
 ls -la gpurun_out
