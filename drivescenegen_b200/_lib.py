@@ -33,6 +33,8 @@ class ConvArgs(C.Structure):
         ("out", C.c_void_p),
         ("block_n", C.c_int32),
         ("impl", C.c_int32),
+        ("out_nchw_f32", C.c_void_p),
+        ("cout_real", C.c_int32),
     ]
 
 

@@ -308,8 +308,8 @@ static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   memset(&p, 0, sizeof(p));
   DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "dsg_conv: bad mode %d", a->mode);
   DSG_CHECK_ARG(a->n >= 0 && a->h > 0 && a->w > 0, "dsg_conv: bad shape");
-  DSG_CHECK_ARG(a->n == 0 || (a->x && a->wpacked && a->out), "dsg_conv: null x/wpacked/out");
-  DSG_CHECK_ARG(a->cin > 0 && a->cin % 64 == 0 && a->cout > 0 && a->cout % 64 == 0,
+  DSG_CHECK_ARG(a->n == 0 || (a->x && a->wpacked && (a->out || a->out_nchw_f32)), "dsg_conv: null x/wpacked/out");
+  DSG_CHECK_ARG(a->cin > 0 && a->cin % 64 == 0 && a->cout > 0 && (a->cout % 64 == 0 || a->out_nchw_f32),
                 "dsg_conv: cin (%d) and cout (%d) must be multiples of 64", a->cin, a->cout);
   DSG_CHECK_ARG(a->csc1 % 64 == 0 && a->csc2 % 64 == 0 && a->csc1 >= 0 && a->csc2 >= 0,
                 "dsg_conv: shortcut channels must be multiples of 64");
@@ -446,6 +446,7 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
   if (a->n == 0) return DSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (a->impl == 1) {
+    DSG_CHECK_ARG(a->out && !a->out_nchw_f32, "dsg_conv: the cross-check kernel writes the h16 NHWC output only");
     p.n_blocks = 1;
     const int64_t total = (int64_t)p.phases * p.N * p.OH * p.OW * p.cout;
     int64_t blocks = ceil_div64(total, 256);
@@ -455,6 +456,14 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
     return DSG_OK;
   }
   DSG_CHECK_ARG(a->impl == 0 || a->impl == 2 || a->impl == 3, "dsg_conv: bad impl %d", a->impl);
+  if (a->out_nchw_f32) {
+    DSG_CHECK_ARG(a->mode == 0 && a->cout == 16 && a->cout_real >= 1 && a->cout_real <= 16 && !a->residual &&
+                      !a->csc1 && a->impl != 2 && (uintptr_t)a->out_nchw_f32 % 4 == 0,
+                  "dsg_conv: conv_out form needs mode 0, cout 16, 1 <= cout_real <= 16, no residual/shortcut");
+    rc = launch_halo_conv(a, 16, st);
+    if (rc == DSG_HALO_SKIP) { set_error("dsg_conv: conv_out form needs W >= 8 and H >= 18"); return DSG_ERR_UNSUPPORTED; }
+    return rc;
+  }
   int bn = a->block_n;
   if (bn == 0) bn = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
   DSG_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && a->cout % bn == 0, "dsg_conv: bad block_n %d for cout %d", bn,

@@ -43,6 +43,8 @@ struct HlPlan {
   int cout, n_blocks;
   int64_t oN, oH, oW;  // output element strides
   __half* out;
+  float* out_f32;      // BLOCK_N = 16 only: NCHW fp32 output of the first cout_real channels (conv_out)
+  int cout_real;
   const __half* res;
   const float* bias;
   const float* temb;
@@ -59,11 +61,12 @@ template <int BLOCK_N, int MT>
 struct HlCfg {
   static constexpr int A_SLOT = MT * 16384 + 4096;  // (MT*8 + 2) rows x 16 px x 128 B (the TW = 8 box is smaller)
   static constexpr int B_SLOT = BLOCK_N * 128;
-  static constexpr int NA = BLOCK_N == 64 ? 4 : (BLOCK_N == 128 ? 3 : 4);
-  static constexpr int NB = BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4);
+  static constexpr int NA = BLOCK_N == 128 ? 3 : 4;
+  static constexpr int NB = BLOCK_N == 16 ? 12 : (BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4));
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
   static constexpr int SMEM_BYTES = RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
+  static_assert(2 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
 };
@@ -210,7 +213,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     const int row = q * 32 + lane;
     const int te = threadIdx.x - 64;
     const int lh0 = row >> p.tw_shift, lw = row & (p.TW - 1);
-    constexpr int NCH = BLOCK_N / 32;
+    constexpr int NCH = BLOCK_N / 32;  // (0 for the BLOCK_N = 16 conv_out form, which has its own epilogue)
     int acc = 0; uint32_t acc_ph = 0;
     for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const HlTile tc = hl_decode(p, t);
@@ -232,6 +235,32 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
 #pragma unroll
           for (int j = 0; j < BLOCK_N; j += 64) prefetch_l2(p.res + off[m] + j);
         }
+      }
+      if constexpr (BLOCK_N == 16) {
+        // conv_out form: the first cout_real accumulator columns go to an NCHW fp32 tensor
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t taddr16 = tmem_base + (uint32_t)(acc * MT * BLOCK_N) + ((uint32_t)(q * 32) << 16);
+        const int64_t plane = (int64_t)p.OH * p.OW;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr16 + (uint32_t)(m * BLOCK_N), v);
+          tmem_ld_wait();
+          if (valid[m]) {
+            const int h = tc.h0 + m * half_rows + lh0, w = tc.w0 + lw;
+            float* op = p.out_f32 + (int64_t)tc.n * p.cout_real * plane + (int64_t)h * p.OW + w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < p.cout_real) op[j * plane] = __uint_as_float(v[j]) + sb[j];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        acc ^= 1; if (acc == 0) acc_ph ^= 1;
+        continue;
       }
       uint4 rnext[4];
       if (p.res && valid[0]) {
@@ -367,6 +396,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   const int out_h = oh * p.omul, out_w = ow * p.omul;
   p.oW = a->cout; p.oH = (int64_t)out_w * a->cout; p.oN = (int64_t)out_h * out_w * a->cout;
   p.out = (__half*)a->out; p.res = (const __half*)a->residual;
+  p.out_f32 = (float*)a->out_nchw_f32; p.cout_real = a->cout_real;
   p.bias = a->bias; p.temb = a->temb; p.temb_stride = a->temb_stride; p.temb_off = a->temb_off;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
   static bool attr_set = false;
@@ -385,6 +415,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
 int launch_halo_conv(const dsg_conv_args* a, int block_n, cudaStream_t st) {
   if (a->mode != 0 && a->mode != 2) return DSG_HALO_SKIP;
   switch (block_n) {
+    case 16: return launch_halo<16, 2>(a, st);
     case 64: return launch_halo<64, 2>(a, st);
     case 128: return launch_halo<128, 2>(a, st);
     case 256: return launch_halo<256, 1>(a, st);

@@ -161,6 +161,15 @@ class UNetEngine:
             self._f32("conv_in.b", sd["conv_in.bias"])
             self._f32("conv_out.w", sd["conv_out.weight"])
             self._f32("conv_out.b", sd["conv_out.bias"])
+            # tensor-core form of conv_out: output channels zero-padded to the smallest UMMA N (16)
+            wo = sd["conv_out.weight"].detach().float()
+            if wo.shape[0] <= 16 and wo.shape[1] % 64 == 0:
+                w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float32)
+                w16[: wo.shape[0]] = wo.cpu()
+                b16 = torch.zeros(16, dtype=torch.float32)
+                b16[: wo.shape[0]] = sd["conv_out.bias"].detach().float().cpu()
+                self._pack_conv("conv_out.w16", 0, w16)
+                self._f32("conv_out.b16", b16)
             self._f32("norm_out.g", sd["conv_norm_out.weight"])
             self._f32("norm_out.b", sd["conv_norm_out.bias"])
             for k in ("linear_1", "linear_2"):
@@ -184,7 +193,16 @@ class UNetEngine:
                 has_sc = sc_key in sd
                 if has_sc != (r["cin"] + r["cskip"] != r["cout"]):
                     raise DsgError(f"{pre}: conv_shortcut presence does not match channel counts")
-                self._pack_conv(f"{pre}.conv2", 0, sd[f"{pre}.conv2.weight"], sd[sc_key] if has_sc else None)
+                # cin == cout blocks have a plain residual.  For narrow outputs (cout <= 128) it rides through the
+                # tensor core as an identity 1x1 shortcut panel (x * 1.0 is exact in fp16, the sum is fp32): the
+                # residual tile then arrives by TMA like every other operand instead of through latency-bound
+                # global loads in the epilogue, which those short-K tiles cannot hide.
+                r["id_sc"] = (not has_sc) and r["cout"] <= 128
+                if r["id_sc"]:
+                    w_sc = torch.eye(r["cout"], dtype=torch.float32)
+                else:
+                    w_sc = sd[sc_key] if has_sc else None
+                self._pack_conv(f"{pre}.conv2", 0, sd[f"{pre}.conv2.weight"], w_sc)
                 b2 = sd[f"{pre}.conv2.bias"].detach().to(self.device, torch.float32)
                 if has_sc:
                     b2 = b2 + sd[f"{pre}.conv_shortcut.bias"].detach().to(self.device, torch.float32)
@@ -295,7 +313,7 @@ class _Program:
         self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
 
     def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
-              sc2=None, csc2=0):
+              sc2=None, csc2=0, count_sc=True):
         eng, lib = self.eng, self.lib
         a = ConvArgs()
         a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, self.b, hw[0], hw[1], cin, cout
@@ -311,7 +329,8 @@ class _Program:
         a.impl = eng.conv_impl
         self.keep.append(a)
         ref = C.byref(a)
-        k_ref = {0: 9 * cin + csc1 + csc2, 1: 9 * cin, 2: 9 * cin, 3: cin}[mode]
+        # reference op count: an identity shortcut panel stands for a residual ADD, not for GEMM work
+        k_ref = {0: 9 * cin + (csc1 + csc2 if count_sc else 0), 1: 9 * cin, 2: 9 * cin, 3: cin}[mode]
         opx = {0: hw[0] * hw[1], 1: hw[0] * hw[1] // 4, 2: hw[0] * hw[1] * 4, 3: hw[0] * hw[1]}[mode]
         meta = {"mode": mode, "hw": hw, "cin": cin + csc1 + csc2, "cout": cout,
                 "flops": 2 * self.b * opx * cout * k_ref}  # algorithmic (reference op count, no sub-pixel discount)
@@ -325,8 +344,9 @@ class _Program:
         self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"])
         act2 = self._tmp("act", hw, co)
         self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2)
-        if r["has_sc"]:
-            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2)
+        if r["has_sc"] or r["id_sc"]:
+            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2,
+                       count_sc=r["has_sc"])
         else:
             self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, residual=x1)
 
@@ -414,10 +434,27 @@ class _Program:
         assert not skips
         act = self._tmp("act", hw, c0)
         self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
-        co_args = (act.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
-        co_tail = (b, c0, hw[0], hw[1], self.cout)
-        self._emit("conv_out", {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2)},
-                   lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
+        tw = 16 if hw[1] >= 16 else (8 if hw[1] >= 8 else 0)
+        meta = {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2), "flops": 2 * b * hw[0] * hw[1] * self.cout * 9 * c0}
+        if "conv_out.w16" in W and tw and hw[0] >= 2 * (128 // tw) + 2 and eng.conv_impl != 1:
+            # tcgen05 path: the halo-reuse igemm with BLOCK_N = 16 and an NCHW fp32 epilogue
+            a = ConvArgs()
+            a.mode, a.n, a.h, a.w, a.cin, a.cout = 0, b, hw[0], hw[1], c0, 16
+            a.x = act.data_ptr()
+            a.wpacked = W["conv_out.w16"].data_ptr()
+            a.bias = W["conv_out.b16"].data_ptr()
+            a.cout_real = self.cout
+            self.keep.append(a)
+
+            def run_conv_out(st, a=a):
+                a.out_nchw_f32 = self.out_ptr.value
+                check(lib.dsg_conv(C.byref(a), st), "conv_out (tcgen05)")
+            self._emit("conv_out", meta, run_conv_out)
+        else:
+            co_args = (act.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
+            co_tail = (b, c0, hw[0], hw[1], self.cout)
+            self._emit("conv_out", meta,
+                       lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
         self.n_launches = len(self.ops) + 1  # time_embed is two launches
 
     def run_timed(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None):

@@ -147,6 +147,26 @@ def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int =
     return out
 
 
+def conv_out_tc(x_nhwc, w, b):
+    """conv_out on the tensor cores: x fp16 NHWC [n,h,w,cin], w fp32 [cout<=16,cin,3,3], b fp32 [cout] -> fp32 NCHW."""
+    _cuda(x_nhwc, w, b)
+    lib = _lib.load()
+    n, h, wd, cin = x_nhwc.shape
+    cout = w.shape[0]
+    w16 = torch.zeros((16, cin, 3, 3), dtype=torch.float32, device=w.device)
+    w16[:cout] = w
+    b16 = torch.zeros(16, dtype=torch.float32, device=w.device)
+    b16[:cout] = b
+    wp = pack_conv_weight(0, w16)
+    out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x_nhwc.device)
+    a = ConvArgs()
+    a.mode, a.n, a.h, a.w, a.cin, a.cout = 0, n, h, wd, cin, 16
+    a.x, a.wpacked, a.bias = x_nhwc.data_ptr(), wp.data_ptr(), b16.data_ptr()
+    a.out_nchw_f32, a.cout_real = out.data_ptr(), cout
+    check(lib.dsg_conv(C.byref(a), _st(x_nhwc)), "dsg_conv (conv_out form)")
+    return out
+
+
 def attention(qkv, heads: int, head_dim: int):
     """qkv fp16 [n, tokens, 3*heads*head_dim] -> fp16 [n, tokens, heads*head_dim]."""
     _cuda(qkv)

@@ -113,6 +113,11 @@ typedef struct dsg_conv_args {
                       1 = plain CUDA-core cross-check kernel (slow; debugging/tests only),
                       2 = force the tap-streaming tcgen05 kernel, 3 = force the halo-reuse tcgen05 kernel
                       (DSG_ERR_UNSUPPORTED when the mode/shape is outside it: modes 0 and 2, W >= 8, H >= tile) */
+  /* conv_out form (replaces UNet2DModel.conv_out, 64 -> 3 channels): when out_nchw_f32 is non-NULL the weights are
+   * packed for cout = 16 (rows >= cout_real are zero), mode must be 0, `out` is ignored and the first cout_real
+   * output channels are written as NCHW fp32 [n][cout_real][h][w].  Halo-reuse kernel only (W >= 8, H >= 18). */
+  void* out_nchw_f32;
+  int32_t cout_real;
 } dsg_conv_args;
 int dsg_conv(const dsg_conv_args* args, void* stream);
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */

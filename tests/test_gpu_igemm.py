@@ -182,3 +182,22 @@ def test_igemm_rejects_bad_args():
     x0 = torch.zeros(0, 8, 8, 64, dtype=torch.float16, device=d)
     wp = torch.zeros(64, 9 * 64, dtype=torch.float16, device=d)
     assert ops.conv(0, x0, wp, 64).shape[0] == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64), (1, 40, 24, 64), (1, 64, 8, 128), (2, 256, 256, 64)])
+def test_conv_out_tensor_core_form(shape):
+    """UNet2DModel.conv_out (C0 -> 3, NHWC fp16 in, NCHW fp32 out) through the BLOCK_N = 16 halo kernel."""
+    from drivescenegen_b200 import ops
+    n, h, w, cin = shape
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    d = _dev()
+    x = torch.randn(n, h, w, cin, generator=g).half()
+    wt = torch.randn(3, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.randn(3, generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.half().float(), b, padding=1)
+    got = ops.conv_out_tc(x.to(d), wt.to(d), b.to(d))
+    torch.cuda.synchronize()
+    err = (got.cpu() - ref).abs().max().item()
+    assert got.shape == ref.shape and err < 2e-3, err
+    old = ops.conv_out(x.to(d), wt.to(d), b.to(d))  # CUDA-core kernel (fp32 weights): same result up to fp16 weights
+    assert (old.cpu() - ref).abs().max().item() < 1e-2
