@@ -35,6 +35,7 @@ class ConvArgs(C.Structure):
         ("impl", C.c_int32),
         ("out_nchw_f32", C.c_void_p),
         ("cout_real", C.c_int32),
+        ("out_stats", C.c_void_p),
     ]
 
 
@@ -53,9 +54,8 @@ SIGNATURES = {
     "dsg_time_embed": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p]),
     "dsg_conv_in": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_conv_out": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
-    "dsg_gn_chunks": (_i32, [_i64]),
-    "dsg_gn_stats": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i64, _i32, _p]),
-    "dsg_gn_apply": (C.c_int, [_p, _i32, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _i64, _i32, _p]),
+    "dsg_gn_stats": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
+    "dsg_gn_apply": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _i64, _i32, _p]),
     "dsg_conv": (C.c_int, [C.POINTER(ConvArgs), _p]),
     "dsg_packed_k": (_i64, [_i32, _i32, _i32]),
     "dsg_packed_rows": (_i64, [_i32, _i32]),

@@ -45,6 +45,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// GroupNorm statistics are exact fixed-point integers (see groupnorm.cu): sum(x) * 2^24 and sum(x^2) * 2^20.
+__device__ __forceinline__ long long gn_fix_sum(float s) { return __float2ll_rn(s * 16777216.0f); }
+__device__ __forceinline__ long long gn_fix_sq(float q) { return __float2ll_rn(q * 1048576.0f); }
+
+// Column sums across a warp: every lane holds v[0..31] (one row of a 32 x 32 block); on return lane j holds
+// sum over lanes of v[j].  Butterfly with halving payload: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float keep = hi ? v[i + off] : v[i];
+      const float send = hi ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -1,44 +1,41 @@
 // groupnorm.cu — GroupNorm(+SiLU) over NHWC fp16 activations, concat-free (two channel-concatenated sources).
 // Replaces torch.nn.GroupNorm(32, C, eps=1e-5) + SiLU inside upstream ResnetBlock2D / Attention / conv_norm_out
 // (diffusers 0.20.0 models/resnet.py, models/attention_processor.py) and the
-// torch.cat([h, skip], dim=1) of UpBlock2D.forward.  HBM-bound: stats = 1 read, apply = 1 read + 1 write.
+// torch.cat([h, skip], dim=1) of UpBlock2D.forward.
+//
+// Statistics are kept PER CHANNEL as exact fixed-point integers: stats[n][c] = { sum(x) * 2^24, sum(x^2) * 2^20 }
+// (int64).  Producers add tile partials with 64-bit integer atomics — associative, so the totals are bit-reproducible
+// whatever the order — either from the conv epilogues (igemm*.cu: the statistics pass then costs no HBM traffic at
+// all) or from gn_stats_kernel below (one read of the tensor; used for conv_in's output and stand-alone calls).
+// Per-channel totals let ONE set of statistics serve every consumer: a skip tensor is normalised once on the way down
+// and once, concatenated with another tensor and therefore with different group boundaries, on the way up.
+// gn_apply_kernel folds the channel totals into group mean / variance in double precision,
+//   var_g = mean_c[ var_c + (mean_c - mean_g)^2 ],  var_c = E[x^2] - E[x]^2 per channel,
+// then streams y = act(x * a_c + b_c): one read + one write of the tensor.
 #include "common.cuh"
 
 namespace dsg {
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_MAX_C = 2048;
 constexpr int GN_ILP = 4;
 
-__device__ __forceinline__ const __half* src_of(const __half* x1, int c1, const __half* x2, int c2, int64_t pix,
-                                                int ch) {
-  return ch < c1 ? x1 + pix * c1 + ch : x2 + pix * c2 + (ch - c1);
-}
-
-// partial[n][chunk][g] = { sum(x - K_g), sum((x - K_g)^2) } with K_g = x[n][pixel 0][first channel of g]
-__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __restrict__ x1, int c1,
-                                                              const __half* __restrict__ x2, int c2,
-                                                              float* __restrict__ partial, int64_t hw, int groups,
+// ------------------------------------------------------------------ per-channel statistics of one tensor
+// grid (chunks, n); thread = (pixel row, 8-channel vector).  Block partials in fp32 (<= ~1024 pixels), totals in int64.
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __restrict__ x, int C,
+                                                              long long* __restrict__ stats, int64_t hw,
                                                               int64_t px_per_chunk) {
-  const int C = c1 + c2, V = C >> 3, cpg = C / groups;
-  const int ppi = GN_THREADS / V;  // pixels per iteration
+  const int V = C >> 3;
+  const int ppi = GN_THREADS / V;  // pixel rows per iteration (V <= 256)
   const int n = blockIdx.y, chunk = blockIdx.x;
-  // per-thread per-channel partials, reduced in a fixed order (deterministic, no atomics)
   __shared__ float s_part[2][GN_THREADS * 8];
   const int64_t base_px = (int64_t)n * hw;
   if ((int)threadIdx.x < ppi * V) {
     const int v = threadIdx.x % V, prow = threadIdx.x / V;
-    const int ch0 = v << 3;
-    float K[8], s[8], q[8];
+    float s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (ch0 + j) / cpg;
-      K[j] = __half2float(*src_of(x1, c1, x2, c2, base_px, g * cpg));
-      s[j] = 0.f; q[j] = 0.f;
-    }
-    const bool from1 = ch0 < c1;  // c1 is a multiple of 8, so a vector never straddles the two sources
-    const __half* src = from1 ? x1 : x2;
-    const int cs = from1 ? c1 : c2, co = from1 ? ch0 : ch0 - c1;
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
     const int64_t p_begin = (int64_t)chunk * px_per_chunk;
     int64_t p_end = p_begin + px_per_chunk;
     if (p_end > hw) p_end = hw;
@@ -48,7 +45,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
 #pragma unroll
       for (int u = 0; u < GN_ILP; ++u) {
         const int64_t pp = p + (int64_t)u * ppi;
-        if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+        if (pp < p_end) raw[u] = ldg_nc_v4(x + (base_px + pp) * C + (v << 3));
       }
 #pragma unroll
       for (int u = 0; u < GN_ILP; ++u) {
@@ -57,37 +54,36 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
           unpack8(raw[u], f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float d = f[j] - K[j];
-            s[j] += d;
-            q[j] = fmaf(d, d, q[j]);
+            s[j] += f[j];
+            q[j] = fmaf(f[j], f[j], q[j]);
           }
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s_part[0][prow * C + ch0 + j] = s[j];
-      s_part[1][prow * C + ch0 + j] = q[j];
+      s_part[0][prow * C + (v << 3) + j] = s[j];
+      s_part[1][prow * C + (v << 3) + j] = q[j];
     }
   }
   __syncthreads();
-  if ((int)threadIdx.x < groups) {
-    const int g = threadIdx.x;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
     float ts = 0.f, tq = 0.f;
-    for (int r = 0; r < ppi; ++r)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ts += s_part[0][r * C + c];
-        tq += s_part[1][r * C + c];
-      }
-    float* o = partial + (((int64_t)n * gridDim.x + chunk) * groups + g) * 2;
-    o[0] = ts;
-    o[1] = tq;
+    for (int r = 0; r < ppi; ++r) {  // fixed order: the block partial is deterministic
+      ts += s_part[0][r * C + c];
+      tq += s_part[1][r * C + c];
+    }
+    long long* o = stats + ((int64_t)n * C + c) * 2;
+    atomicAdd(reinterpret_cast<unsigned long long*>(o), (unsigned long long)gn_fix_sum(ts));
+    atomicAdd(reinterpret_cast<unsigned long long*>(o + 1), (unsigned long long)gn_fix_sq(tq));
   }
 }
 
+// ------------------------------------------------------------------ normalise + affine + activation
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __restrict__ x1, int c1,
+                                                              const long long* __restrict__ st1,
                                                               const __half* __restrict__ x2, int c2,
-                                                              const float* __restrict__ partial, int chunks,
+                                                              const long long* __restrict__ st2,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int act,
                                                               __half* __restrict__ y, int64_t hw, int groups,
@@ -95,23 +91,30 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int ppi = GN_THREADS / V;
   const int n = blockIdx.y;
+  __shared__ float s_m[GN_MAX_C], s_v[GN_MAX_C];  // per-channel mean / variance
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  const int64_t base_px = (int64_t)n * hw;
+  const double inv_hw = 1.0 / (double)hw;
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const long long* sp = c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2;
+    const double m = (double)sp[0] * (1.0 / 16777216.0) * inv_hw;
+    const double var = (double)sp[1] * (1.0 / 1048576.0) * inv_hw - m * m;
+    s_m[c] = (float)m;
+    s_v[c] = (float)(var > 0.0 ? var : 0.0);
+  }
+  __syncthreads();
   if ((int)threadIdx.x < groups) {
     const int g = threadIdx.x;
-    double S1 = 0.0, S2 = 0.0;
-    const float* p = partial + ((int64_t)n * chunks * groups + g) * 2;
-    for (int c = 0; c < chunks; ++c) {
-      S1 += (double)p[(int64_t)c * groups * 2];
-      S2 += (double)p[(int64_t)c * groups * 2 + 1];
+    double mg = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) mg += (double)s_m[c];
+    mg /= (double)cpg;
+    double vg = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const double d = (double)s_m[c] - mg;
+      vg += (double)s_v[c] + d * d;
     }
-    const double cnt = (double)hw * cpg;
-    const double K = (double)__half2float(*src_of(x1, c1, x2, c2, base_px, g * cpg));
-    const double m1 = S1 / cnt;
-    double var = S2 / cnt - m1 * m1;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = (float)(K + m1);
-    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    vg /= (double)cpg;
+    s_mean[g] = (float)mg;
+    s_rstd[g] = (float)(1.0 / sqrt(vg + (double)eps));
   }
   __syncthreads();
   if ((int)threadIdx.x >= ppi * V) return;
@@ -124,9 +127,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
     a[j] = gamma[ch] * s_rstd[g];
     b[j] = beta[ch] - s_mean[g] * a[j];
   }
-  const bool from1 = ch0 < c1;
+  const bool from1 = ch0 < c1;  // c1 is a multiple of 8, so a vector never straddles the two sources
   const __half* src = from1 ? x1 : x2;
   const int cs = from1 ? c1 : c2, co = from1 ? ch0 : ch0 - c1;
+  const int64_t base_px = (int64_t)n * hw;
   const int64_t p_begin = (int64_t)blockIdx.x * px_per_cta;
   int64_t p_end = p_begin + px_per_cta;
   if (p_end > hw) p_end = hw;
@@ -154,58 +158,55 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   }
 }
 
-static int gn_check(const void* x1, int c1, const void* x2, int c2, int n, int64_t hw, int groups, const char* who) {
-  DSG_CHECK_ARG(x1 && c1 > 0 && c1 % 8 == 0, "%s: x1 null or c1 not a multiple of 8", who);
-  DSG_CHECK_ARG((x2 == nullptr) == (c2 == 0) && c2 % 8 == 0, "%s: x2/c2 mismatch", who);
-  const int C = c1 + c2;
-  DSG_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "%s: bad groups %d for C=%d", who, groups, C);
-  DSG_CHECK_ARG(C / 8 <= GN_THREADS, "%s: C=%d too large (max %d)", who, C, GN_THREADS * 8);
-  DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "%s: bad n/hw", who);
-  DSG_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2) % 16 == 0, "%s: pointers must be 16-byte aligned", who);
-  return DSG_OK;
-}
-
 }  // namespace dsg
 
 using namespace dsg;
 
 extern "C" {
 
-int32_t dsg_gn_chunks(int64_t hw) {
-  int64_t c = ceil_div64(hw, 64);
-  if (c > 64) c = 64;
-  if (c < 1) c = 1;
-  return (int32_t)c;
-}
-
-int dsg_gn_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, float* partial, int32_t n, int64_t hw,
-                 int32_t groups, void* stream) {
-  int rc = gn_check(x1, c1, x2, c2, n, hw, groups, "dsg_gn_stats");
-  if (rc) return rc;
-  DSG_CHECK_ARG(partial, "dsg_gn_stats: partial is null");
+int dsg_gn_stats(const void* x, int32_t c, void* stats, int32_t n, int64_t hw, void* stream) {
+  DSG_CHECK_ARG(x && stats && c > 0 && c % 8 == 0 && c <= GN_MAX_C, "dsg_gn_stats: null pointer or bad c=%d", c);
+  DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_stats: bad n/hw");
+  DSG_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)stats % 8 == 0, "dsg_gn_stats: unaligned pointer");
   if (n == 0) return DSG_OK;
-  const int chunks = dsg_gn_chunks(hw);
+  // chunks of <= ~1024 pixels keep the fp32 block partials accurate; at least ~4 blocks per SM for bandwidth
+  int64_t chunks = ceil_div64(hw, 1024);
+  const int64_t want = ceil_div64(148 * 4, n);
+  if (chunks < want) chunks = want;
+  const int64_t max_chunks = ceil_div64(hw, 32);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks > 65535) chunks = 65535;
   const int64_t ppc = ceil_div64(hw, chunks);
-  gn_stats_kernel<<<dim3(chunks, n), GN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)x1, c1, (const __half*)x2,
-                                                                            c2, partial, hw, groups, ppc);
+  chunks = ceil_div64(hw, ppc);
+  gn_stats_kernel<<<dim3((unsigned)chunks, n), GN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)x, c,
+                                                                                      (long long*)stats, hw, ppc);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_stats");
   return DSG_OK;
 }
 
-int dsg_gn_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* partial, const float* gamma,
-                 const float* beta, float eps, int32_t act, void* y, int32_t n, int64_t hw, int32_t groups,
-                 void* stream) {
-  int rc = gn_check(x1, c1, x2, c2, n, hw, groups, "dsg_gn_apply");
-  if (rc) return rc;
-  DSG_CHECK_ARG(partial && gamma && beta && y && (uintptr_t)y % 16 == 0, "dsg_gn_apply: null/unaligned pointer");
+int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2, const void* stats2,
+                 const float* gamma, const float* beta, float eps, int32_t act, void* y, int32_t n, int64_t hw,
+                 int32_t groups, void* stream) {
+  DSG_CHECK_ARG(x1 && stats1 && c1 > 0 && c1 % 8 == 0, "dsg_gn_apply: x1/stats1 null or c1 not a multiple of 8");
+  DSG_CHECK_ARG((x2 == nullptr) == (c2 == 0) && (x2 == nullptr) == (stats2 == nullptr) && c2 % 8 == 0,
+                "dsg_gn_apply: x2/stats2/c2 mismatch");
+  const int C = c1 + c2;
+  DSG_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "dsg_gn_apply: bad groups %d for C=%d",
+                groups, C);
+  DSG_CHECK_ARG(C <= GN_MAX_C, "dsg_gn_apply: C=%d too large (max %d)", C, GN_MAX_C);
+  DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_apply: bad n/hw");
+  DSG_CHECK_ARG(gamma && beta && y, "dsg_gn_apply: null pointer");
+  DSG_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)y) % 16 == 0 &&
+                    ((uintptr_t)stats1 | (uintptr_t)stats2) % 8 == 0,
+                "dsg_gn_apply: unaligned pointer");
   if (n == 0) return DSG_OK;
-  const int V = (c1 + c2) / 8, ppi = GN_THREADS / V;
-  int64_t px_per_cta = (int64_t)ppi * 16;
+  const int V = C / 8, ppi = GN_THREADS / V;
+  int64_t px_per_cta = (int64_t)ppi * 4 * GN_ILP;
   int64_t ctas = ceil_div64(hw, px_per_cta);
   if (ctas > 65535) { px_per_cta = ceil_div64(hw, 65535); ctas = ceil_div64(hw, px_per_cta); }
   gn_apply_kernel<<<dim3((unsigned)ctas, n), GN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __half*)x1, c1, (const __half*)x2, c2, partial, dsg_gn_chunks(hw), gamma, beta, eps, act, (__half*)y, hw,
-      groups, px_per_cta);
+      (const __half*)x1, c1, (const long long*)stats1, (const __half*)x2, c2, (const long long*)stats2, gamma, beta,
+      eps, act, (__half*)y, hw, groups, px_per_cta);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_apply");
   return DSG_OK;
 }

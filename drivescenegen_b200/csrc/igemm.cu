@@ -40,6 +40,7 @@ struct IgPlan {
   const float* bias;
   const float* temb;
   int temb_stride, temb_off;
+  long long* stats;   // optional per-channel GroupNorm totals of the output: int64 [N][cout][2] (groupnorm.cu)
   int a_bytes;        // bytes one A box delivers (TH clipped to the image height)
   int64_t total_tiles;
 };
@@ -54,7 +55,8 @@ struct IgCfg {
   static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 256 -> 4, 128 -> 6, 64 -> 8
   static constexpr int TMEM_COLS = 2 * BLOCK_N;              // double-buffered fp32 accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 8 /*GN stats*/ +
+                                    256 /*barriers*/ + 1024 /*align*/;
 };
 
 struct TileCoord {
@@ -81,7 +83,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   float* sbias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 2 * BLOCK_N);
+  float* sstat = sbias + 2 * BLOCK_N;                                          // [4][BLOCK_N][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * BLOCK_N);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -189,8 +192,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
+        float f[32];
         if (valid) {
-          float f[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
@@ -212,11 +215,19 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
           __half* op = p.out + off + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
         }
+        if (p.stats) epi_stats_slice(f, sstat + (q * BLOCK_N + c * 32) * 2, lane, true);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_stats_flush<BLOCK_N>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
+      }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
   }
@@ -260,6 +271,11 @@ __global__ void __launch_bounds__(256) igemm_naive_kernel(const __grid_constant_
     const int64_t off = (int64_t)n * p.oN + (int64_t)(h * p.omul + pa) * p.oH + (int64_t)(w * p.omul + pb) * p.oW + co;
     if (p.res) acc += __half2float(p.res[off]);
     p.out[off] = __float2half_rn(acc);
+    if (p.stats) {
+      long long* o = p.stats + ((int64_t)n * p.cout + co) * 2;
+      atomicAdd(reinterpret_cast<unsigned long long*>(o), (unsigned long long)gn_fix_sum(acc));
+      atomicAdd(reinterpret_cast<unsigned long long*>(o + 1), (unsigned long long)gn_fix_sq(acc * acc));
+    }
   }
 }
 
@@ -378,6 +394,7 @@ static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   p.oW = a->cout; p.oH = (int64_t)out_w * a->cout; p.oN = (int64_t)out_h * out_w * a->cout;
   p.w = (const __half*)a->wpacked; p.out = (__half*)a->out; p.res = (const __half*)a->residual;
   p.bias = a->bias; p.temb = a->temb; p.temb_stride = a->temb_stride; p.temb_off = a->temb_off;
+  p.stats = (long long*)a->out_stats;
   return DSG_OK;
 }
 

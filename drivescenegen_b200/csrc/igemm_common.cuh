@@ -14,6 +14,37 @@ struct IgSrc {
   int C, H, W;         // logical extents (out-of-range reads are zero)
 };
 
+// ------------------------------------------------------------------ GroupNorm statistics in the conv epilogue
+// Each epilogue warp owns 32 accumulator rows.  Per 32-column slice it reduces its rows to per-column sum / sum of
+// squares (warp butterfly) and keeps them in its private quarter of sstat[4][BLOCK_N][2]; after the tile the four
+// quarters are combined in a fixed order and added to the tensor's per-channel int64 totals (groupnorm.cu).
+__device__ __forceinline__ void epi_stats_slice(const float* f, float* sstat_warp_slice /* [32][2] */, int lane,
+                                                bool first) {
+  float t[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = f[j];
+  const float s1 = warp_colsum32(t, lane);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = f[j] * f[j];
+  const float s2 = warp_colsum32(t, lane);
+  float2* slot = reinterpret_cast<float2*>(sstat_warp_slice) + lane;
+  if (first) {
+    *slot = make_float2(s1, s2);
+  } else {
+    float2 o = *slot;
+    *slot = make_float2(o.x + s1, o.y + s2);
+  }
+}
+template <int BLOCK_N>
+__device__ __forceinline__ void epi_stats_flush(const float* sstat /* [4][BLOCK_N][2] */, int te /* 0..127 */,
+                                                long long* stats_nc /* &stats[(n * cout + n0) * 2] */) {
+  for (int idx = te; idx < 2 * BLOCK_N; idx += 128) {
+    const float v = ((sstat[idx] + sstat[2 * BLOCK_N + idx]) + sstat[4 * BLOCK_N + idx]) + sstat[6 * BLOCK_N + idx];
+    const long long fx = (idx & 1) ? gn_fix_sq(v) : gn_fix_sum(v);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats_nc + idx), (unsigned long long)fx);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

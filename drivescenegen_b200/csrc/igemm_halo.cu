@@ -49,6 +49,7 @@ struct HlPlan {
   const float* bias;
   const float* temb;
   int temb_stride, temb_off;
+  long long* stats;    // optional per-channel GroupNorm totals of the output: int64 [N][cout][2] (groupnorm.cu)
   int64_t total_tiles;
 };
 
@@ -65,7 +66,8 @@ struct HlCfg {
   static constexpr int NB = BLOCK_N == 16 ? 12 : (BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4));
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
-  static constexpr int SMEM_BYTES = RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES =
+      RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 8 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
   static_assert(2 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
@@ -100,7 +102,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + NA * Cfg::A_SLOT;
   float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);  // [2][BLOCK_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 2 * BLOCK_N);
+  float* sstat = sbias + 2 * BLOCK_N;                               // [4][BLOCK_N][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * BLOCK_N);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NA;
   uint64_t* b_full = a_empty + NA;
@@ -290,8 +293,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
             }
           }
           tmem_ld_wait();
+          float f[32];
           if (valid[m]) {
-            float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
@@ -312,12 +315,20 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
             __half* op = p.out + off[m] + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
           }
+          if (p.stats) epi_stats_slice(f, sstat + (q * BLOCK_N + c * 32) * 2, lane, m == 0);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_stats_flush<BLOCK_N>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
+      }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
   }
@@ -398,6 +409,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.out = (__half*)a->out; p.res = (const __half*)a->residual;
   p.out_f32 = (float*)a->out_nchw_f32; p.cout_real = a->cout_real;
   p.bias = a->bias; p.temb = a->temb; p.temb_stride = a->temb_stride; p.temb_off = a->temb_off;
+  p.stats = (long long*)a->out_stats;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
   static bool attr_set = false;
   if (!attr_set) {

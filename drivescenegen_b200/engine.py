@@ -271,17 +271,35 @@ class _Program:
         self.cout = int(eng.cfg.get("out_channels", 3))
         # pass 1 sizes the shared temporaries (so no buffer is outgrown mid-program), pass 2 emits the ops
         self._measure: Optional[Dict[Tuple[str, torch.dtype], int]] = {}
+        self._stats_off = 0
+        self.stats_all: Optional[torch.Tensor] = None   # every GroupNorm-statistics slice of this program, contiguous
+        self.stats_of: Dict[int, torch.Tensor] = {}     # activation buffer (data_ptr) -> its int64 [b][C][2] totals
         self._build()
         for (name, dtype), numel in self._measure.items():
             eng.arena.get(name, numel, dtype)
         self._measure = None
+        self.stats_all = eng.arena.get(f"{batch}x{h}x{w}/gn_stats", max(self._stats_off, 2), torch.int64)
+        self._stats_off = 0
+        self.stats_of = {}
         self.ops, self.keep, self.op_info = [], [], []
         self._build()
 
     # --- buffers -------------------------------------------------------------------------------------
+    def _stats(self, ch: int) -> torch.Tensor:
+        """A fresh int64 [b][ch][2] slice of per-channel GroupNorm totals (zeroed once per run with all the others)."""
+        n = self.b * ch * 2
+        off = self._stats_off
+        self._stats_off += n
+        if self.stats_all is None:     # measuring pass
+            return self.eng.arena.get("tmp/_measure_i64", 16, torch.int64)
+        return self.stats_all[off:off + n]
+
     def _new(self, name: str, hw: Tuple[int, int], ch: int) -> torch.Tensor:
+        """A persistent activation buffer; whichever conv writes it also accumulates its GroupNorm statistics."""
         numel = self.b * hw[0] * hw[1] * ch
-        return self.eng.arena.get(f"{self.b}x{self.h}x{self.w}/{name}", numel, torch.float16)
+        t = self.eng.arena.get(f"{self.b}x{self.h}x{self.w}/{name}", numel, torch.float16)
+        self.stats_of[t.data_ptr()] = self._stats(ch)
+        return t
 
     def _tmp_raw(self, name: str, numel: int, dtype) -> torch.Tensor:
         # temporaries are shared by name across layers (and shapes): sized to the largest request
@@ -299,21 +317,21 @@ class _Program:
         self.ops.append(fn)
         self.op_info.append((name, meta))
 
-    def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out):
+    def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out, st1=None, st2=None):
+        """GroupNorm(+SiLU) of cat(x1, x2); the statistics were accumulated by whoever produced x1 / x2."""
         eng, lib, b = self.eng, self.lib, self.b
         npx = hw[0] * hw[1]
-        chunks = lib.dsg_gn_chunks(npx)
-        part = self._tmp_raw("gn_partial", b * chunks * eng.groups * 2, torch.float32)
+        st1 = st1 if st1 is not None else self.stats_of[x1.data_ptr()]
+        if x2 is not None and st2 is None:
+            st2 = self.stats_of[x2.data_ptr()]
         g, bt = eng.weights[gname], eng.weights[bname]
-        a1 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), b, npx, eng.groups)
-        a2 = (_p(x1), c1, _p(x2), c2, part.data_ptr(), g.data_ptr(), bt.data_ptr(), eng.eps, act, out.data_ptr(), b,
-              npx, eng.groups)
+        a2 = (_p(x1), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps, act,
+              out.data_ptr(), b, npx, eng.groups)
         nbytes = b * npx * (c1 + c2) * 2
-        self._emit("gn_stats", {"bytes": nbytes}, lambda st, a=a1: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
         self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
 
     def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
-              sc2=None, csc2=0, count_sc=True):
+              sc2=None, csc2=0, count_sc=True, stats=None):
         eng, lib = self.eng, self.lib
         a = ConvArgs()
         a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, self.b, hw[0], hw[1], cin, cout
@@ -325,6 +343,9 @@ class _Program:
             a.temb, a.temb_stride, a.temb_off = self.temb.data_ptr(), eng.proj_total, temb_off
         a.residual = _p(residual)
         a.out = out.data_ptr()
+        stats = stats if stats is not None else self.stats_of.get(out.data_ptr())
+        if stats is not None:
+            a.out_stats = stats.data_ptr()   # the epilogue accumulates the next GroupNorm's statistics
         a.block_n = eng.block_n_override if (eng.block_n_override and cout % eng.block_n_override == 0) else 0
         a.impl = eng.conv_impl
         self.keep.append(a)
@@ -341,9 +362,11 @@ class _Program:
         act = self._tmp("act", hw, c1 + c2)
         self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
         hbuf = self._tmp("h", hw, co)
-        self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"])
+        h_stats = self._stats(co)   # the "h" buffer is shared between blocks, its statistics are not
+        self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"],
+                   stats=h_stats)
         act2 = self._tmp("act", hw, co)
-        self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2)
+        self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2, st1=h_stats)
         if r["has_sc"] or r["id_sc"]:
             self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2,
                        count_sc=r["has_sc"])
@@ -377,12 +400,17 @@ class _Program:
                    W["te.linear_2.w"].data_ptr(), W["te.linear_2.b"].data_ptr(), eng.temb_hidden,
                    W["te.proj.w"].data_ptr(), W["te.proj.b"].data_ptr(), eng.proj_total, emb_ws.data_ptr(),
                    self.temb.data_ptr(), b)
+        self._emit("zero_stats", {}, lambda st: self.stats_all.zero_())
         self._emit("time_embed", {}, lambda st: check(lib.dsg_time_embed(self.t_ptr, *te_args, st), "time_embed"))
         c0 = eng.cfg["block_out_channels"][0]
         x = self._new("conv_in", hw, c0)
         ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(), b, self.cin, hw[0], hw[1], c0)
         self._emit("conv_in", {"bytes": b * hw[0] * hw[1] * (self.cin * 4 + c0 * 2)},
                    lambda st: check(lib.dsg_conv_in(self.in_ptr, *ci_args, st), "conv_in"))
+        # conv_in is a CUDA-core kernel without the statistics epilogue: one read of its output instead
+        gs_args = (x.data_ptr(), c0, self.stats_of[x.data_ptr()].data_ptr(), b, hw[0] * hw[1])
+        self._emit("gn_stats", {"bytes": b * hw[0] * hw[1] * c0 * 2},
+                   lambda st: check(lib.dsg_gn_stats(*gs_args, st), "gn_stats"))
         skips = [(x, c0, hw)]
         for i, blk in enumerate(eng.down):
             for j, r in enumerate(blk["resnets"]):
@@ -455,7 +483,7 @@ class _Program:
             co_tail = (b, c0, hw[0], hw[1], self.cout)
             self._emit("conv_out", meta,
                        lambda st: check(lib.dsg_conv_out(*co_args, self.out_ptr, *co_tail, st), "conv_out"))
-        self.n_launches = len(self.ops) + 1  # time_embed is two launches
+        self.n_launches = len(self.ops) + 1  # time_embed is two launches (zero_stats is one fill kernel)
 
     def run_timed(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None):
         """Eager replay with a CUDA-event pair around every launch; returns [(name, meta, milliseconds)]."""

@@ -92,19 +92,30 @@ def conv_out(x_nhwc, w, b):
     return out
 
 
-def group_norm(x1, x2, gamma, beta, groups: int, eps: float, act: int):
-    """x1 [n,h,w,c1] (+ x2 [n,h,w,c2]) fp16 NHWC -> fp16 [n,h,w,c1+c2]."""
+def gn_stats(x):
+    """Per-channel GroupNorm totals of x fp16 NHWC [n,h,w,c]: int64 [n,c,2] = {sum * 2^24, sum of squares * 2^20}."""
+    _cuda(x)
+    lib = _lib.load()
+    n, h, w, c = x.shape
+    st = torch.zeros((n, c, 2), dtype=torch.int64, device=x.device)
+    check(lib.dsg_gn_stats(x.data_ptr(), c, st.data_ptr(), n, h * w, _st(x)), "gn_stats")
+    return st
+
+
+def group_norm(x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=None, stats2=None):
+    """x1 [n,h,w,c1] (+ x2 [n,h,w,c2]) fp16 NHWC -> fp16 [n,h,w,c1+c2].  stats: see gn_stats / conv(out_stats=)."""
     _cuda(x1, x2, gamma, beta)
     lib = _lib.load()
     n, h, w, c1 = x1.shape
     c2 = 0 if x2 is None else x2.shape[3]
     hw = h * w
-    chunks = lib.dsg_gn_chunks(hw)
-    part = torch.empty((n, chunks, groups, 2), dtype=torch.float32, device=x1.device)
+    if stats1 is None:
+        stats1 = gn_stats(x1)
+    if x2 is not None and stats2 is None:
+        stats2 = gn_stats(x2)
     y = torch.empty((n, h, w, c1 + c2), dtype=torch.float16, device=x1.device)
-    check(lib.dsg_gn_stats(x1.data_ptr(), c1, _p(x2), c2, part.data_ptr(), n, hw, groups, _st(x1)), "gn_stats")
-    check(lib.dsg_gn_apply(x1.data_ptr(), c1, _p(x2), c2, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, act,
-                           y.data_ptr(), n, hw, groups, _st(x1)), "gn_apply")
+    check(lib.dsg_gn_apply(x1.data_ptr(), c1, stats1.data_ptr(), _p(x2), c2, _p(stats2), gamma.data_ptr(),
+                           beta.data_ptr(), eps, act, y.data_ptr(), n, hw, groups, _st(x1)), "gn_apply")
     return y
 
 
@@ -124,8 +135,9 @@ def pack_conv_weight(mode: int, w, w_sc=None):
 
 
 def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int = 0, residual=None, sc1=None, sc2=None,
-         block_n: int = 0, impl: int = 0):
-    """x fp16 NHWC [n,h,w,cin]; returns fp16 NHWC [n,oh,ow,cout] (see dsg_conv in include/dsg_b200.h)."""
+         block_n: int = 0, impl: int = 0, out_stats=None):
+    """x fp16 NHWC [n,h,w,cin]; returns fp16 NHWC [n,oh,ow,cout] (see dsg_conv in include/dsg_b200.h).
+    out_stats: optional zeroed int64 [n,cout,2] tensor that receives the output's GroupNorm totals."""
     _cuda(x, wpacked, bias, temb, residual, sc1, sc2)
     lib = _lib.load()
     n, h, w, cin = x.shape
@@ -143,6 +155,7 @@ def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int =
     a.residual = _p(residual)
     a.out = out.data_ptr()
     a.block_n, a.impl = block_n, impl
+    a.out_stats = _p(out_stats)
     check(lib.dsg_conv(C.byref(a), _st(x)), "dsg_conv")
     return out
 

@@ -75,16 +75,15 @@ int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, i
 int dsg_conv_out(const void* x_h16, const float* w, const float* b, float* out, int32_t n, int32_t cin, int32_t h,
                  int32_t wd, int32_t cout, void* stream);
 
-/* GroupNorm statistics over the channel-concatenation of up to two h16 tensors (x1 has c1 channels, x2 has c2,
- * x2 may be NULL).  partial: float[n][chunks][groups][2] shifted sums; chunks is returned by
- * dsg_gn_chunks(hw).  Deterministic (no atomics). */
-int32_t dsg_gn_chunks(int64_t hw);
-int dsg_gn_stats(const void* x1, int32_t c1, const void* x2, int32_t c2, float* partial, int32_t n, int64_t hw,
-                 int32_t groups, void* stream);
+/* GroupNorm over the channel-concatenation of up to two h16 tensors (x1 has c1 channels, x2 has c2, x2 may be NULL).
+ * Statistics are per-channel fixed-point totals: stats int64 [n][c][2] = { sum(x) * 2^24, sum(x^2) * 2^20 },
+ * accumulated with integer atomics (order-independent, bit-reproducible).  They come either from dsg_conv's
+ * epilogue (out_stats) or from dsg_gn_stats, which ADDS one tensor's totals to a caller-zeroed buffer. */
+int dsg_gn_stats(const void* x, int32_t c, void* stats, int32_t n, int64_t hw, void* stream);
 /* y = act(GroupNorm(cat(x1,x2))) written as ONE h16 tensor with c1+c2 channels; act: 0 none, 1 SiLU. */
-int dsg_gn_apply(const void* x1, int32_t c1, const void* x2, int32_t c2, const float* partial, const float* gamma,
-                 const float* beta, float eps, int32_t act, void* y, int32_t n, int64_t hw, int32_t groups,
-                 void* stream);
+int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2, const void* stats2,
+                 const float* gamma, const float* beta, float eps, int32_t act, void* y, int32_t n, int64_t hw,
+                 int32_t groups, void* stream);
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores (TMA -> smem -> UMMA -> TMEM -> epilogue).
  * mode: 0 = 3x3 stride 1 pad 1, 1 = 3x3 stride 2 pad 1, 2 = nearest-2x upsample followed by 3x3 pad 1
@@ -118,6 +117,9 @@ typedef struct dsg_conv_args {
    * output channels are written as NCHW fp32 [n][cout_real][h][w].  Halo-reuse kernel only (W >= 8, H >= 18). */
   void* out_nchw_f32;
   int32_t cout_real;
+  /* optional: per-channel GroupNorm totals of the OUTPUT, int64 [n][cout][2] = { sum * 2^24, sum of squares * 2^20 },
+   * ADDED to (zero the buffer first) from the epilogue — the statistics pass of the next GroupNorm for free. */
+  void* out_stats;
 } dsg_conv_args;
 int dsg_conv(const dsg_conv_args* args, void* stream);
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */

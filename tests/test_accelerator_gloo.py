@@ -37,8 +37,10 @@ WORKER = textwrap.dedent("""
             acc.clip_grad_norm_(model.parameters(), 1.0)
             opt.step(); sched.step(); opt.zero_grad()
     flat = torch.cat([p.detach().flatten() for p in model.parameters()])
-    print("RESULT " + json.dumps({"rank": rank, "seen": seen, "w": flat.tolist(), "lr": sched.get_last_lr()[0],
-                                   "allreduce_calls": calls["n"], "len": len(loader)}), flush=True)
+    # one file per rank: two ranks sharing one stdout pipe can interleave inside a line
+    with open(os.path.join(os.environ["DSG_OUT"], f"rank{rank}.json"), "w") as f:
+        json.dump({"rank": rank, "seen": seen, "w": flat.tolist(), "lr": sched.get_last_lr()[0],
+                   "allreduce_calls": calls["n"], "len": len(loader)}, f)
     dist.barrier(); dist.destroy_process_group()
 """)
 
@@ -47,14 +49,12 @@ def test_two_rank_gradient_averaging(tmp_path):
     import json
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, DSG_ROOT=ROOT, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    env = dict(os.environ, DSG_ROOT=ROOT, DSG_OUT=str(tmp_path), CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29631", str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
-    res = sorted((json.loads(l[7:]) for l in out.stdout.splitlines() if l.startswith("RESULT ")),
-                 key=lambda r: r["rank"])
-    assert len(res) == 2
+    res = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     # round-robin sharding: rank 0 sees batches 0,2,4 and rank 1 sees 1,3,5 (first column identifies the rows)
     assert res[0]["len"] == 3 and len(res[0]["seen"]) == 3 and len(res[1]["seen"]) == 3
     assert res[0]["seen"][0][0] == 0.0 and abs(res[1]["seen"][0][0] - 0.8) < 1e-6

@@ -201,3 +201,43 @@ def test_conv_out_tensor_core_form(shape):
     assert got.shape == ref.shape and err < 2e-3, err
     old = ops.conv_out(x.to(d), wt.to(d), b.to(d))  # CUDA-core kernel (fp32 weights): same result up to fp16 weights
     assert (old.cpu() - ref).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("case", [
+    # mode, n, h, w, cin, cout, impl
+    (0, 2, 32, 32, 64, 64, 3), (0, 2, 40, 24, 128, 128, 3), (0, 1, 32, 32, 128, 256, 3), (0, 3, 16, 16, 64, 64, 2),
+    (1, 2, 32, 32, 64, 128, 2), (2, 2, 32, 32, 64, 64, 3), (3, 2, 16, 16, 128, 256, 2), (0, 2, 32, 32, 64, 64, 1),
+])
+def test_conv_epilogue_groupnorm_stats(case):
+    """out_stats: per-channel int64 totals {sum * 2^24, sum of squares * 2^20} of the conv output, from the epilogue."""
+    from drivescenegen_b200 import ops
+    mode, n, h, w, cin, cout, impl = case
+    g = torch.Generator().manual_seed(sum(case))
+    d = _dev()
+    x = torch.randn(n, h, w, cin, generator=g).half().to(d)
+    ksz = 1 if mode == 3 else 3
+    wt = torch.randn(cout, cin, ksz, ksz, generator=g) / (cin * ksz * ksz) ** 0.5
+    if mode == 3:
+        wt = wt.view(cout, cin)
+    b = (torch.randn(cout, generator=g) + 1.5).to(d)   # non-zero mean
+    wp = ops.pack_conv_weight(mode, wt.to(d))
+    st = torch.zeros(n, cout, 2, dtype=torch.int64, device=d)
+    y = ops.conv(mode, x, wp, cout, bias=b, impl=impl, out_stats=st)
+    st2 = torch.zeros_like(st)
+    y2 = ops.conv(mode, x, wp, cout, bias=b, impl=impl, out_stats=st2)
+    torch.cuda.synchronize()
+    assert torch.equal(st, st2) and torch.equal(y, y2), "integer totals must be bit-reproducible"
+    yf = y.double()
+    s1 = st[..., 0].double().cpu() / 2 ** 24
+    s2 = st[..., 1].double().cpu() / 2 ** 20
+    r1 = yf.sum(dim=(1, 2)).cpu()
+    r2 = (yf * yf).sum(dim=(1, 2)).cpu()
+    # the epilogue sums the fp32 values BEFORE the fp16 rounding of the stored tensor: agree to ~fp16 rounding noise
+    npx = y.shape[1] * y.shape[2]
+    assert (s1 - r1).abs().max().item() < 2e-3 * npx ** 0.5 + 1e-2, (s1 - r1).abs().max()
+    assert ((s2 - r2).abs() / r2).max().item() < 2e-3, ((s2 - r2).abs() / r2).max()
+    # and they drive GroupNorm to the same result as statistics taken from the stored tensor
+    gamma, beta = torch.randn(cout, generator=g).to(d), torch.randn(cout, generator=g).to(d)
+    a = ops.group_norm(y, None, gamma, beta, 32, 1e-5, 1, stats1=st)
+    bref = ops.group_norm(y, None, gamma, beta, 32, 1e-5, 1)
+    assert (a.float() - bref.float()).abs().max().item() < 4e-3

@@ -30,7 +30,6 @@ def test_cabi_exports_every_declared_symbol(built_lib):
     assert set(_lib.SIGNATURES) == declared
     l = _lib.load()
     assert l.dsg_version() == 100
-    assert l.dsg_gn_chunks(65536) == 64 and l.dsg_gn_chunks(16) == 1
     assert l.dsg_packed_k(0, 64, 128) == 9 * 64 + 128 and l.dsg_packed_k(2, 64, 0) == 256
     assert l.dsg_packed_rows(2, 64) == 256
 
