@@ -61,6 +61,7 @@ SIGNATURES = {
     "dsg_packed_rows": (_i64, [_i32, _i32]),
     "dsg_pack_conv_weight": (C.c_int, [_i32, _p, _i32, _i32, _p, _i32, _p, _p]),
     "dsg_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dsg_attention_ex": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p]),
 }
 
 _lib = None

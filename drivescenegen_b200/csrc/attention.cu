@@ -123,13 +123,27 @@ static int launch_attention(const __half* qkv, __half* out, int n, int tokens, i
 
 using namespace dsg;
 
-extern "C" int dsg_attention(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
-                             void* stream) {
+namespace dsg {
+int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int heads, int head_dim, float* dbg,
+                        cudaStream_t st);  // attention_tc.cu
+}
+
+extern "C" int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads,
+                                int32_t head_dim, int32_t impl, float* dbg, void* stream) {
   DSG_CHECK_ARG(qkv && out, "dsg_attention: null pointer");
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && tokens > 0 && heads > 0 && heads <= 65535, "dsg_attention: bad shape");
   DSG_CHECK_ARG(((uintptr_t)qkv | (uintptr_t)out) % 16 == 0, "dsg_attention: pointers must be 16-byte aligned");
+  DSG_CHECK_ARG(impl >= 0 && impl <= 2, "dsg_attention: bad impl %d", impl);
   if (n == 0) return DSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl != 1) {
+    const int rc = launch_attention_tc((const __half*)qkv, (__half*)out, n, tokens, heads, head_dim, dbg, st);
+    if (rc <= 0) return rc;
+    if (impl == 2) {
+      dsg::set_error("dsg_attention: the tcgen05 kernel needs head_dim 8 and 128 <= tokens <= 4096, tokens %% 128 == 0");
+      return DSG_ERR_UNSUPPORTED;
+    }
+  }
   switch (head_dim) {
     case 8: return launch_attention<8>((const __half*)qkv, (__half*)out, n, tokens, heads, st);
     case 16: return launch_attention<16>((const __half*)qkv, (__half*)out, n, tokens, heads, st);
@@ -139,4 +153,9 @@ extern "C" int dsg_attention(const void* qkv, void* out, int32_t n, int32_t toke
       dsg::set_error("dsg_attention: head_dim %d unsupported (8/16/32/64)", head_dim);
       return DSG_ERR_UNSUPPORTED;
   }
+}
+
+extern "C" int dsg_attention(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
+                             void* stream) {
+  return dsg_attention_ex(qkv, out, n, tokens, heads, head_dim, 0, nullptr, stream);
 }

@@ -9,16 +9,17 @@
 // all) or from gn_stats_kernel below (one read of the tensor; used for conv_in's output and stand-alone calls).
 // Per-channel totals let ONE set of statistics serve every consumer: a skip tensor is normalised once on the way down
 // and once, concatenated with another tensor and therefore with different group boundaries, on the way up.
-// gn_apply_kernel folds the channel totals into group mean / variance in double precision,
-//   var_g = mean_c[ var_c + (mean_c - mean_g)^2 ],  var_c = E[x^2] - E[x]^2 per channel,
-// then streams y = act(x * a_c + b_c): one read + one write of the tensor.
+// (The tcgen05 epilogues store the totals of each channel PAIR in the even channel's slot — half the shuffles — so
+// consumers may only sum whole groups; group sizes and source widths are even whenever that path is used.)
+// gn_apply_kernel sums the integer totals of each group exactly, forms mean / variance in double precision and
+// streams y = act(x * a_c + b_c): one read + one write of the tensor.
 #include "common.cuh"
 
 namespace dsg {
 
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
-constexpr int GN_MAX_C = 2048;
+constexpr int GN_MAX_C = 2048;  // 256 threads x 8 channels
 constexpr int GN_ILP = 4;
 
 // ------------------------------------------------------------------ per-channel statistics of one tensor
@@ -91,28 +92,21 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int ppi = GN_THREADS / V;
   const int n = blockIdx.y;
-  __shared__ float s_m[GN_MAX_C], s_v[GN_MAX_C];  // per-channel mean / variance
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  const double inv_hw = 1.0 / (double)hw;
-  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-    const long long* sp = c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2;
-    const double m = (double)sp[0] * (1.0 / 16777216.0) * inv_hw;
-    const double var = (double)sp[1] * (1.0 / 1048576.0) * inv_hw - m * m;
-    s_m[c] = (float)m;
-    s_v[c] = (float)(var > 0.0 ? var : 0.0);
-  }
-  __syncthreads();
   if ((int)threadIdx.x < groups) {
+    // exact integer totals of the group's channels (only whole groups are ever summed: conv epilogues store
+    // channel PAIRS in the even slot), then mean / variance in double
     const int g = threadIdx.x;
-    double mg = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) mg += (double)s_m[c];
-    mg /= (double)cpg;
-    double vg = 0.0;
+    long long t1 = 0, t2 = 0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const double d = (double)s_m[c] - mg;
-      vg += (double)s_v[c] + d * d;
+      const long long* sp = c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2;
+      t1 += sp[0];
+      t2 += sp[1];
     }
-    vg /= (double)cpg;
+    const double inv_cnt = 1.0 / ((double)hw * (double)cpg);
+    const double mg = (double)t1 * (1.0 / 16777216.0) * inv_cnt;
+    double vg = (double)t2 * (1.0 / 1048576.0) * inv_cnt - mg * mg;
+    if (vg < 0.0) vg = 0.0;
     s_mean[g] = (float)mg;
     s_rstd[g] = (float)(1.0 / sqrt(vg + (double)eps));
   }

@@ -55,7 +55,7 @@ struct IgCfg {
   static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 256 -> 4, 128 -> 6, 64 -> 8
   static constexpr int TMEM_COLS = 2 * BLOCK_N;              // double-buffered fp32 accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 8 /*GN stats*/ +
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 4 /*GN stats*/ +
                                     256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -83,8 +83,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   float* sbias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
-  float* sstat = sbias + 2 * BLOCK_N;                                          // [4][BLOCK_N][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * BLOCK_N);
+  float* sstat = sbias + 2 * BLOCK_N;                                          // [4][BLOCK_N / 2][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 4 * BLOCK_N);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -183,44 +183,11 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
       tc_fence_after();
       const int lh = row >> p.tw_shift, lw = row & (p.TW - 1);
       const int h = tc.h0 + lh, w = tc.w0 + lw;
-      const bool valid = (h < p.OH) && (w < p.OW);
-      const int64_t off = (int64_t)tc.n * p.oN + (int64_t)(h * p.omul + tc.pa) * p.oH +
-                          (int64_t)(w * p.omul + tc.pb) * p.oW + n0;
+      const bool valid[1] = {(h < p.OH) && (w < p.OW)};
+      const int64_t off[1] = {(int64_t)tc.n * p.oN + (int64_t)(h * p.omul + tc.pa) * p.oH +
+                              (int64_t)(w * p.omul + tc.pb) * p.oW + n0};
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        float f[32];
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (p.res) {
-            const __half* rp = p.res + off + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float r[8];
-              unpack8(ldg_nc_v4(rp + j), r);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) f[j + u] += r[u];
-            }
-          }
-          __half* op = p.out + off + c * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
-        }
-        if (p.stats) epi_stats_slice(f, sstat + (q * BLOCK_N + c * 32) * 2, lane, true);
-      }
+      epi_tile<BLOCK_N, 1>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);

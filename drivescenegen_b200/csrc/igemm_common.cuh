@@ -14,34 +14,118 @@ struct IgSrc {
   int C, H, W;         // logical extents (out-of-range reads are zero)
 };
 
-// ------------------------------------------------------------------ GroupNorm statistics in the conv epilogue
-// Each epilogue warp owns 32 accumulator rows.  Per 32-column slice it reduces its rows to per-column sum / sum of
-// squares (warp butterfly) and keeps them in its private quarter of sstat[4][BLOCK_N][2]; after the tile the four
-// quarters are combined in a fixed order and added to the tensor's per-channel int64 totals (groupnorm.cu).
-__device__ __forceinline__ void epi_stats_slice(const float* f, float* sstat_warp_slice /* [32][2] */, int lane,
-                                                bool first) {
-  float t[32];
+// ------------------------------------------------------------------ shared epilogue (TMEM -> fp16 NHWC + GN stats)
+// GroupNorm statistics ride along for free-ish: every epilogue warp owns 32 accumulator rows; per 32-column slice it
+// adds adjacent channel PAIRS in registers (summed over the MT stacked accumulators first), reduces the 16 pair sums
+// across its 32 rows with a halving butterfly (16 shuffles per statistic) and parks them in its quarter of
+// sstat[4][BLOCK_N / 2][2].  After the tile the four quarters are combined in a fixed order and added to the tensor's
+// int64 totals (groupnorm.cu) in the EVEN channel's slot — consumers only ever sum whole groups, and group sizes
+// are even whenever this path is used (the engine falls back to dsg_gn_stats otherwise).
+
+// a[0..15], b[0..15]: per-lane pair sums of two statistics.  On return a[0], b[0] hold the warp totals of pair
+// (lane >> 1) (identical in lanes 2k and 2k + 1).  The two chains are independent and interleave.
+__device__ __forceinline__ void warp_pairsum16x2(float* a, float* b, int lane) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) t[j] = f[j];
-  const float s1 = warp_colsum32(t, lane);
+  for (int off = 16; off >= 2; off >>= 1) {
+    const int n = off >> 1;
+    const bool hi = (lane & off) != 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) t[j] = f[j] * f[j];
-  const float s2 = warp_colsum32(t, lane);
-  float2* slot = reinterpret_cast<float2*>(sstat_warp_slice) + lane;
-  if (first) {
-    *slot = make_float2(s1, s2);
-  } else {
-    float2 o = *slot;
-    *slot = make_float2(o.x + s1, o.y + s2);
+    for (int i = 0; i < n; ++i) {
+      const float ka = hi ? a[i + n] : a[i], sa = hi ? a[i] : a[i + n];
+      const float kb = hi ? b[i + n] : b[i], sb = hi ? b[i] : b[i + n];
+      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+      b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+}
+
+// One CTA tile of the epilogue for one warp (32 rows): MT stacked accumulators of BLOCK_N fp32 columns each at
+// taddr (+ m * BLOCK_N), slice by slice (c outer, m inner).  The tcgen05.ld of the next slice is in flight while
+// the current one is converted; the residual (if any) is register-prefetched one slice ahead.
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const bool (&valid)[MT],
+                                         const int64_t (&off)[MT], __half* out, const __half* res,
+                                         float* sstat_warp /* [BLOCK_N / 2][2] or nullptr */, int lane) {
+  constexpr int NCH = BLOCK_N / 32, NIT = NCH * MT;
+  uint32_t v[2][32];
+  uint4 rn[4];
+  if (res && valid[0]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rn[j] = ldg_nc_v4(res + off[0] + j * 8);
+  }
+  tmem_ld_32x32(taddr, v[0]);
+  float a1[16], a2[16];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int c = it / MT, m = it % MT;
+    tmem_ld_wait();
+    if (it + 1 < NIT) {
+      const int nc = (it + 1) / MT, nm = (it + 1) % MT;
+      tmem_ld_32x32(taddr + (uint32_t)(nm * BLOCK_N + nc * 32), v[(it + 1) & 1]);
+    }
+    uint4 rc[4];
+    if (res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rc[j] = rn[j];
+      if (it + 1 < NIT) {
+        const int nc = (it + 1) / MT, nm = (it + 1) % MT;
+        if (valid[nm]) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rn[j] = ldg_nc_v4(res + off[nm] + nc * 32 + j * 8);
+        }
+      }
+    }
+    float f[32];
+    if (valid[m]) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+        f[j] = __uint_as_float(v[it & 1][j]) + b4.x;
+        f[j + 1] = __uint_as_float(v[it & 1][j + 1]) + b4.y;
+        f[j + 2] = __uint_as_float(v[it & 1][j + 2]) + b4.z;
+        f[j + 3] = __uint_as_float(v[it & 1][j + 3]) + b4.w;
+      }
+      if (res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r[8];
+          unpack8(rc[j], r);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[j * 8 + u] += r[u];
+        }
+      }
+      __half* op = out + off[m] + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
+    }
+    if (sstat_warp) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x0 = f[2 * j], x1 = f[2 * j + 1];
+        const float s = x0 + x1, qq = fmaf(x0, x0, x1 * x1);
+        if (m == 0) { a1[j] = s; a2[j] = qq; } else { a1[j] += s; a2[j] += qq; }
+      }
+      if (m == MT - 1) {
+        warp_pairsum16x2(a1, a2, lane);
+        if (!(lane & 1)) reinterpret_cast<float2*>(sstat_warp)[c * 16 + (lane >> 1)] = make_float2(a1[0], a2[0]);
+      }
+    }
   }
 }
+
+// combine the four warps' pair totals (fixed order) and add them to the tensor's int64 totals
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_stats_flush(const float* sstat /* [4][BLOCK_N][2] */, int te /* 0..127 */,
+__device__ __forceinline__ void epi_stats_flush(const float* sstat /* [4][BLOCK_N / 2][2] */, int te /* 0..127 */,
                                                 long long* stats_nc /* &stats[(n * cout + n0) * 2] */) {
-  for (int idx = te; idx < 2 * BLOCK_N; idx += 128) {
-    const float v = ((sstat[idx] + sstat[2 * BLOCK_N + idx]) + sstat[4 * BLOCK_N + idx]) + sstat[6 * BLOCK_N + idx];
+  for (int idx = te; idx < BLOCK_N; idx += 128) {
+    const float v = ((sstat[idx] + sstat[BLOCK_N + idx]) + sstat[2 * BLOCK_N + idx]) + sstat[3 * BLOCK_N + idx];
     const long long fx = (idx & 1) ? gn_fix_sq(v) : gn_fix_sum(v);
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats_nc + idx), (unsigned long long)fx);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats_nc + (idx >> 1) * 4 + (idx & 1)), (unsigned long long)fx);
   }
 }
 

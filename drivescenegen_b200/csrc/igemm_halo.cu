@@ -67,7 +67,7 @@ struct HlCfg {
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
   static constexpr int SMEM_BYTES =
-      RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 8 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
+      RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
   static_assert(2 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
@@ -102,8 +102,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + NA * Cfg::A_SLOT;
   float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);  // [2][BLOCK_N]
-  float* sstat = sbias + 2 * BLOCK_N;                               // [4][BLOCK_N][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 8 * BLOCK_N);
+  float* sstat = sbias + 2 * BLOCK_N;                               // [4][BLOCK_N / 2][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 4 * BLOCK_N);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NA;
   uint64_t* b_full = a_empty + NA;
@@ -216,7 +216,6 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     const int row = q * 32 + lane;
     const int te = threadIdx.x - 64;
     const int lh0 = row >> p.tw_shift, lw = row & (p.TW - 1);
-    constexpr int NCH = BLOCK_N / 32;  // (0 for the BLOCK_N = 16 conv_out form, which has its own epilogue)
     int acc = 0; uint32_t acc_ph = 0;
     for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const HlTile tc = hl_decode(p, t);
@@ -265,63 +264,12 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
         continue;
       }
-      uint4 rnext[4];
-      if (p.res && valid[0]) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rnext[j] = ldg_nc_v4(p.res + off[0] + j * 8);
-      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * MT * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-#pragma unroll 1
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + (uint32_t)(m * BLOCK_N + c * 32), v);
-          uint4 rcur[4];
-          if (p.res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
-            // prefetch the next 32-column slice of the residual (next chunk, or chunk 0 of the next accumulator)
-            const int nm = (c + 1 < NCH) ? m : m + 1, nc = (c + 1 < NCH) ? c + 1 : 0;
-            if (nm < MT && valid[nm < MT ? nm : 0]) {
-              const __half* rp = p.res + off[nm < MT ? nm : 0] + nc * 32;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rnext[j] = ldg_nc_v4(rp + j * 8);
-            }
-          }
-          tmem_ld_wait();
-          float f[32];
-          if (valid[m]) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
-              f[j] = __uint_as_float(v[j]) + b4.x;
-              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-            }
-            if (p.res) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float r[8];
-                unpack8(rcur[j], r);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) f[j * 8 + u] += r[u];
-              }
-            }
-            __half* op = p.out + off[m] + c * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
-          }
-          if (p.stats) epi_stats_slice(f, sstat + (q * BLOCK_N + c * 32) * 2, lane, m == 0);
-        }
-      }
+      if constexpr (BLOCK_N >= 32)
+        epi_tile<BLOCK_N, MT>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);

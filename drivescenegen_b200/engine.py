@@ -324,6 +324,18 @@ class _Program:
         st1 = st1 if st1 is not None else self.stats_of[x1.data_ptr()]
         if x2 is not None and st2 is None:
             st2 = self.stats_of[x2.data_ptr()]
+        if ((c1 + c2) // eng.groups) % 2:
+            # odd group size: the conv epilogues' channel-pair totals do not line up with the groups, so take
+            # per-channel statistics with one extra read of each source instead
+            srcs = [(x1, c1)] + ([(x2, c2)] if x2 is not None else [])
+            fresh = []
+            for xs, cs in srcs:
+                stx = self._stats(cs)
+                fresh.append(stx)
+                ga = (xs.data_ptr(), cs, stx.data_ptr(), b, npx)
+                self._emit("gn_stats", {"bytes": b * npx * cs * 2},
+                           lambda st, a=ga: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
+            st1, st2 = fresh[0], (fresh[1] if len(fresh) > 1 else None)
         g, bt = eng.weights[gname], eng.weights[bname]
         a2 = (_p(x1), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps, act,
               out.data_ptr(), b, npx, eng.groups)

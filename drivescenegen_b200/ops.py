@@ -180,11 +180,12 @@ def conv_out_tc(x_nhwc, w, b):
     return out
 
 
-def attention(qkv, heads: int, head_dim: int):
-    """qkv fp16 [n, tokens, 3*heads*head_dim] -> fp16 [n, tokens, heads*head_dim]."""
-    _cuda(qkv)
+def attention(qkv, heads: int, head_dim: int, impl: int = 0, dbg=None):
+    """qkv fp16 [n, tokens, 3*heads*head_dim] -> fp16 [n, tokens, heads*head_dim] (see dsg_attention_ex)."""
+    _cuda(qkv, dbg)
     lib = _lib.load()
     n, tokens, c3 = qkv.shape
     out = torch.empty((n, tokens, c3 // 3), dtype=torch.float16, device=qkv.device)
-    check(lib.dsg_attention(qkv.data_ptr(), out.data_ptr(), n, tokens, heads, head_dim, _st(qkv)), "attention")
+    check(lib.dsg_attention_ex(qkv.data_ptr(), out.data_ptr(), n, tokens, heads, head_dim, impl, _p(dbg), _st(qkv)),
+          "attention")
     return out

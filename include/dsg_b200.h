@@ -118,7 +118,9 @@ typedef struct dsg_conv_args {
   void* out_nchw_f32;
   int32_t cout_real;
   /* optional: per-channel GroupNorm totals of the OUTPUT, int64 [n][cout][2] = { sum * 2^24, sum of squares * 2^20 },
-   * ADDED to (zero the buffer first) from the epilogue — the statistics pass of the next GroupNorm for free. */
+   * ADDED to (zero the buffer first) from the epilogue — the statistics pass of the next GroupNorm for free.
+   * The tcgen05 kernels store the total of channels (2k, 2k+1) in channel 2k's slot and leave 2k+1's untouched:
+   * valid for dsg_gn_apply whenever the group size and c1 are even (it only sums whole groups). */
   void* out_stats;
 } dsg_conv_args;
 int dsg_conv(const dsg_conv_args* args, void* stream);
@@ -134,6 +136,12 @@ int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_
  * out h16 [n][tokens][c]; softmax(q k^T / sqrt(head_dim)) v per head.  head_dim must be 8, 16, 32 or 64. */
 int dsg_attention(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
                   void* stream);
+/* Same with an explicit implementation: impl 0 = auto (tcgen05 kernel for head_dim 8 and tokens a multiple of 128 up
+ * to 4096, else the CUDA-core flash kernel), 1 = CUDA-core kernel, 2 = tcgen05 kernel or DSG_ERR_UNSUPPORTED.
+ * dbg (tests; may be NULL): float[128*128 + 128*16] receives the raw scores of the first 128 x 128 block and the
+ * un-normalised output tile (column 8 = softmax denominator) of the first (sample, head). */
+int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
+                     int32_t impl, float* dbg, void* stream);
 
 #ifdef __cplusplus
 }

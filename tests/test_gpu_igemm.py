@@ -228,10 +228,15 @@ def test_conv_epilogue_groupnorm_stats(case):
     torch.cuda.synchronize()
     assert torch.equal(st, st2) and torch.equal(y, y2), "integer totals must be bit-reproducible"
     yf = y.double()
-    s1 = st[..., 0].double().cpu() / 2 ** 24
-    s2 = st[..., 1].double().cpu() / 2 ** 20
-    r1 = yf.sum(dim=(1, 2)).cpu()
-    r2 = (yf * yf).sum(dim=(1, 2)).cpu()
+    # the tcgen05 epilogues keep channel-PAIR totals in the even slot (odd slot untouched); the cross-check kernel
+    # is per channel: compare pair totals
+    pair = lambda t: t[:, 0::2] + t[:, 1::2]
+    if impl != 1:
+        assert int(st[:, 1::2].abs().max()) == 0
+    s1 = pair(st[..., 0].double().cpu()) / 2 ** 24
+    s2 = pair(st[..., 1].double().cpu()) / 2 ** 20
+    r1 = pair(yf.sum(dim=(1, 2)).cpu())
+    r2 = pair((yf * yf).sum(dim=(1, 2)).cpu())
     # the epilogue sums the fp32 values BEFORE the fp16 rounding of the stored tensor: agree to ~fp16 rounding noise
     npx = y.shape[1] * y.shape[2]
     assert (s1 - r1).abs().max().item() < 2e-3 * npx ** 0.5 + 1e-2, (s1 - r1).abs().max()
