@@ -93,6 +93,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   const int ppi = GN_THREADS / V;
   const int n = blockIdx.y;
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const bool active = (int)threadIdx.x < ppi * V;
+  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  const int ch0 = v << 3;
+  const bool from1 = ch0 < c1;  // c1 is a multiple of 8, so a vector never straddles the two sources
+  const __half* src = from1 ? x1 : x2;
+  const int cs = from1 ? c1 : c2, co = from1 ? ch0 : ch0 - c1;
+  const int64_t base_px = (int64_t)n * hw;
+  const int64_t p_begin = (int64_t)blockIdx.x * px_per_cta;
+  int64_t p_end = p_begin + px_per_cta;
+  if (p_end > hw) p_end = hw;
+  // the first batch of loads does not depend on the statistics: put it in flight before the prologue
+  uint4 raw[GN_ILP];
+  int64_t p = p_begin + prow;
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < GN_ILP; ++u) {
+      const int64_t pp = p + (int64_t)u * ppi;
+      if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+    }
+  }
   if ((int)threadIdx.x < groups) {
     // exact integer totals of the group's channels (only whole groups are ever summed: conv epilogues store
     // channel PAIRS in the even slot), then mean / variance in double
@@ -111,9 +131,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
     s_rstd[g] = (float)(1.0 / sqrt(vg + (double)eps));
   }
   __syncthreads();
-  if ((int)threadIdx.x >= ppi * V) return;
-  const int v = threadIdx.x % V, prow = threadIdx.x / V;
-  const int ch0 = v << 3;
+  if (!active) return;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -121,19 +139,13 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
     a[j] = gamma[ch] * s_rstd[g];
     b[j] = beta[ch] - s_mean[g] * a[j];
   }
-  const bool from1 = ch0 < c1;  // c1 is a multiple of 8, so a vector never straddles the two sources
-  const __half* src = from1 ? x1 : x2;
-  const int cs = from1 ? c1 : c2, co = from1 ? ch0 : ch0 - c1;
-  const int64_t base_px = (int64_t)n * hw;
-  const int64_t p_begin = (int64_t)blockIdx.x * px_per_cta;
-  int64_t p_end = p_begin + px_per_cta;
-  if (p_end > hw) p_end = hw;
-  for (int64_t p = p_begin + prow; p < p_end; p += (int64_t)ppi * GN_ILP) {
-    uint4 raw[GN_ILP];
+  while (p < p_end) {
+    const int64_t pn = p + (int64_t)ppi * GN_ILP;
+    uint4 nxt[GN_ILP];
 #pragma unroll
-    for (int u = 0; u < GN_ILP; ++u) {
-      const int64_t pp = p + (int64_t)u * ppi;
-      if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+    for (int u = 0; u < GN_ILP; ++u) {  // next batch in flight while this one is converted
+      const int64_t pp = pn + (int64_t)u * ppi;
+      if (pp < p_end) nxt[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
     }
 #pragma unroll
     for (int u = 0; u < GN_ILP; ++u) {
@@ -149,6 +161,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
         stg_v4(y + (base_px + pp) * C + ch0, pack8(f));
       }
     }
+#pragma unroll
+    for (int u = 0; u < GN_ILP; ++u) raw[u] = nxt[u];
+    p = pn;
   }
 }
 
@@ -195,7 +210,12 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
                 "dsg_gn_apply: unaligned pointer");
   if (n == 0) return DSG_OK;
   const int V = C / 8, ppi = GN_THREADS / V;
-  int64_t px_per_cta = (int64_t)ppi * 4 * GN_ILP;
+  // about one full wave of CTAs (3 per SM at 74 registers) for big tensors — the per-CTA prologue is amortised and there is no
+  // tail wave — but never less than one batch of loads per thread
+  const int64_t batch_px = (int64_t)ppi * GN_ILP;
+  int64_t per_sample = (148 * 3) / n;
+  if (per_sample < 1) per_sample = 1;
+  int64_t px_per_cta = ceil_div64(ceil_div64(hw, per_sample), batch_px) * batch_px;
   int64_t ctas = ceil_div64(hw, px_per_cta);
   if (ctas > 65535) { px_per_cta = ceil_div64(hw, 65535); ctas = ceil_div64(hw, px_per_cta); }
   gn_apply_kernel<<<dim3((unsigned)ctas, n), GN_THREADS, 0, (cudaStream_t)stream>>>(

@@ -7,11 +7,13 @@ namespace dsg {
 
 constexpr int TE_THREADS = 256;
 
-// grid = batch.  emb_ws[b][:] = SiLU(linear_2(SiLU(linear_1(sinusoid(t[b])))))
+// grid = batch, one thread per output feature.  emb_ws[b][:] = SiLU(linear_2(SiLU(linear_1(sinusoid(t[b]))))).
+// Weights come TRANSPOSED ([in][out]) so that consecutive threads read consecutive addresses and every thread runs
+// an independent, unrollable dot product (the [out][in] + warp-reduction form was a chain of dependent latencies).
 __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __restrict__ t,
                                                               const float* __restrict__ freqs, int half, int flip,
-                                                              const float* __restrict__ w1, const float* __restrict__ b1,
-                                                              const float* __restrict__ w2, const float* __restrict__ b2,
+                                                              const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                              const float* __restrict__ w2t, const float* __restrict__ b2,
                                                               int hidden, float* __restrict__ emb_ws) {
   extern __shared__ float sm[];
   float* e = sm;               // [2*half]
@@ -26,25 +28,28 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     e[flip ? i : half + i] = c;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int r = warp; r < hidden; r += nwarp) {
-    float acc = 0.f;
-    for (int k = lane; k < in_dim; k += 32) acc = fmaf(w1[(int64_t)r * in_dim + k], e[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float y = acc + b1[r];
-      h1[r] = y / (1.0f + expf(-y));
+  for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 4 <= in_dim; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(w1t[(int64_t)(k + u) * hidden + r], e[k + u], acc[u]);
     }
+    for (; k < in_dim; ++k) acc[0] = fmaf(w1t[(int64_t)k * hidden + r], e[k], acc[0]);
+    const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b1[r];
+    h1[r] = y / (1.0f + expf(-y));
   }
   __syncthreads();
-  for (int r = warp; r < hidden; r += nwarp) {
-    float acc = 0.f;
-    for (int k = lane; k < hidden; k += 32) acc = fmaf(w2[(int64_t)r * hidden + k], h1[k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float y = acc + b2[r];
-      emb_ws[(int64_t)b * hidden + r] = y / (1.0f + expf(-y));
+  for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 4 <= hidden; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(w2t[(int64_t)(k + u) * hidden + r], h1[k + u], acc[u]);
     }
+    for (; k < hidden; ++k) acc[0] = fmaf(w2t[(int64_t)k * hidden + r], h1[k], acc[0]);
+    const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b2[r];
+    emb_ws[(int64_t)b * hidden + r] = y / (1.0f + expf(-y));
   }
 }
 
@@ -89,16 +94,16 @@ __global__ void __launch_bounds__(TE_THREADS) temb_proj_kernel(const float* __re
 using namespace dsg;
 
 extern "C" int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos,
-                              const float* w1, const float* b1, const float* w2, const float* b2, int32_t hidden,
+                              const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t hidden,
                               const float* wp, const float* bp, int32_t proj_total, float* emb_ws, float* out,
                               int32_t batch, void* stream) {
-  DSG_CHECK_ARG(t && freqs && w1 && b1 && w2 && b2 && wp && bp && emb_ws && out, "dsg_time_embed: null pointer");
+  DSG_CHECK_ARG(t && freqs && w1t && b1 && w2t && b2 && wp && bp && emb_ws && out, "dsg_time_embed: null pointer");
   DSG_CHECK_ARG(half > 0 && hidden > 0 && hidden <= 2048 && proj_total > 0 && batch >= 0,
                 "dsg_time_embed: bad sizes");
   if (batch == 0) return DSG_OK;
   const size_t sm1 = (size_t)(2 * half + hidden) * sizeof(float);
-  temb_mlp_kernel<<<batch, TE_THREADS, sm1, (cudaStream_t)stream>>>(t, freqs, half, flip_sin_to_cos, w1, b1, w2, b2,
-                                                                    hidden, emb_ws);
+  temb_mlp_kernel<<<batch, TE_THREADS, sm1, (cudaStream_t)stream>>>(t, freqs, half, flip_sin_to_cos, w1t, b1, w2t,
+                                                                    b2, hidden, emb_ws);
   DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/mlp");
   const size_t sm2 = (size_t)TP_BT * hidden * sizeof(float);
   if (sm2 > 48 * 1024)

@@ -173,7 +173,7 @@ class UNetEngine:
             self._f32("norm_out.g", sd["conv_norm_out.weight"])
             self._f32("norm_out.b", sd["conv_norm_out.bias"])
             for k in ("linear_1", "linear_2"):
-                self._f32(f"te.{k}.w", sd[f"time_embedding.{k}.weight"])
+                self._f32(f"te.{k}.w", sd[f"time_embedding.{k}.weight"].t())   # [in][out]: see dsg_time_embed
                 self._f32(f"te.{k}.b", sd[f"time_embedding.{k}.bias"])
             self._f32("te.proj.w", torch.cat([sd[r["prefix"] + ".time_emb_proj.weight"] for r in self.resnets], 0))
             self._f32("te.proj.b", torch.cat([sd[r["prefix"] + ".time_emb_proj.bias"] for r in self.resnets], 0))

@@ -64,8 +64,9 @@ def time_embed(t, freqs, flip, w1, b1, w2, b2, wp, bp):
     batch, hidden, proj = t.numel(), w1.shape[0], wp.shape[0]
     emb = torch.empty((batch, hidden), dtype=torch.float32, device=t.device)
     out = torch.empty((batch, proj), dtype=torch.float32, device=t.device)
-    check(lib.dsg_time_embed(t.data_ptr(), freqs.data_ptr(), freqs.numel(), int(flip), w1.data_ptr(), b1.data_ptr(),
-                             w2.data_ptr(), b2.data_ptr(), hidden, wp.data_ptr(), bp.data_ptr(), proj, emb.data_ptr(),
+    w1t, w2t = w1.t().contiguous(), w2.t().contiguous()   # the C ABI takes [in][out]
+    check(lib.dsg_time_embed(t.data_ptr(), freqs.data_ptr(), freqs.numel(), int(flip), w1t.data_ptr(), b1.data_ptr(),
+                             w2t.data_ptr(), b2.data_ptr(), hidden, wp.data_ptr(), bp.data_ptr(), proj, emb.data_ptr(),
                              out.data_ptr(), batch, _st(t)), "time_embed")
     return out, emb
 

@@ -62,10 +62,11 @@ int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, in
 /* ---------------------------------------------------------------- U-Net building blocks ------------------- */
 /* Timesteps + TimestepEmbedding + all per-ResnetBlock time_emb_proj in two launches.
  *   t: float[batch] (timestep values), freqs: float[half] (exp table, host-computed like upstream),
- *   w1 [hidden][2*half], b1, w2 [hidden][hidden], b2, wp [proj_total][hidden], bp [proj_total]  (all fp32)
+ *   w1t [2*half][hidden], w2t [hidden][hidden]: the two TimestepEmbedding weights TRANSPOSED ([in][out]), b1, b2,
+ *   wp [proj_total][hidden], bp [proj_total]  (all fp32)
  *   emb_ws: float[batch][hidden] scratch; out: float[batch][proj_total] = Linear(SiLU(emb)) per block. */
-int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos, const float* w1,
-                   const float* b1, const float* w2, const float* b2, int32_t hidden, const float* wp,
+int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos, const float* w1t,
+                   const float* b1, const float* w2t, const float* b2, int32_t hidden, const float* wp,
                    const float* bp, int32_t proj_total, float* emb_ws, float* out, int32_t batch, void* stream);
 
 /* conv_in: NCHW fp32 [n][cin][h][w] (cin <= 4) -> h16 [n][h][w][cout]; 3x3, pad 1.  w: fp32 [cout][cin][3][3]. */

@@ -239,7 +239,7 @@ def test_conv_epilogue_groupnorm_stats(case):
     r2 = pair((yf * yf).sum(dim=(1, 2)).cpu())
     # the epilogue sums the fp32 values BEFORE the fp16 rounding of the stored tensor: agree to ~fp16 rounding noise
     npx = y.shape[1] * y.shape[2]
-    assert (s1 - r1).abs().max().item() < 2e-3 * npx ** 0.5 + 1e-2, (s1 - r1).abs().max()
+    assert (s1 - r1).abs().max().item() < 4e-3 * npx ** 0.5 + 2e-2, (s1 - r1).abs().max()
     assert ((s2 - r2).abs() / r2).max().item() < 2e-3, ((s2 - r2).abs() / r2).max()
     # and they drive GroupNorm to the same result as statistics taken from the stored tensor
     gamma, beta = torch.randn(cout, generator=g).to(d), torch.randn(cout, generator=g).to(d)
