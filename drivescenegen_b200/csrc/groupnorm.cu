@@ -113,19 +113,26 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
       if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
     }
   }
-  if ((int)threadIdx.x < groups) {
-    // exact integer totals of the group's channels (only whole groups are ever summed: conv epilogues store
-    // channel PAIRS in the even slot), then mean / variance in double
-    const int g = threadIdx.x;
-    long long t1 = 0, t2 = 0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      const long long* sp = c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2;
-      t1 += sp[0];
-      t2 += sp[1];
+  // exact integer totals per group (only whole groups are ever summed: conv epilogues store channel PAIRS in the even
+  // slot).  Every thread fetches whole channels in ONE round of loads and adds them with shared-memory integer
+  // atomics — order-independent — instead of 32 threads walking their group's channels one dependent load at a time.
+  __shared__ unsigned long long s_t[GN_MAX_GROUPS][2];
+  if ((int)threadIdx.x < groups) { s_t[threadIdx.x][0] = 0ull; s_t[threadIdx.x][1] = 0ull; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const longlong2 tv = *reinterpret_cast<const longlong2*>(
+        c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2);
+    if (tv.x != 0 || tv.y != 0) {
+      atomicAdd(&s_t[c / cpg][0], (unsigned long long)tv.x);
+      atomicAdd(&s_t[c / cpg][1], (unsigned long long)tv.y);
     }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
     const double inv_cnt = 1.0 / ((double)hw * (double)cpg);
-    const double mg = (double)t1 * (1.0 / 16777216.0) * inv_cnt;
-    double vg = (double)t2 * (1.0 / 1048576.0) * inv_cnt - mg * mg;
+    const double mg = (double)(long long)s_t[g][0] * (1.0 / 16777216.0) * inv_cnt;
+    double vg = (double)(long long)s_t[g][1] * (1.0 / 1048576.0) * inv_cnt - mg * mg;
     if (vg < 0.0) vg = 0.0;
     s_mean[g] = (float)mg;
     s_rstd[g] = (float)(1.0 / sqrt(vg + (double)eps));
@@ -206,7 +213,7 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_apply: bad n/hw");
   DSG_CHECK_ARG(gamma && beta && y, "dsg_gn_apply: null pointer");
   DSG_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)y) % 16 == 0 &&
-                    ((uintptr_t)stats1 | (uintptr_t)stats2) % 8 == 0,
+                    ((uintptr_t)stats1 | (uintptr_t)stats2) % 16 == 0,
                 "dsg_gn_apply: unaligned pointer");
   if (n == 0) return DSG_OK;
   const int V = C / 8, ppi = GN_THREADS / V;

@@ -439,12 +439,12 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
     DSG_CUDA_LAUNCH_CHECK("dsg_conv/naive");
     return DSG_OK;
   }
-  DSG_CHECK_ARG(a->impl == 0 || a->impl == 2 || a->impl == 3, "dsg_conv: bad impl %d", a->impl);
+  DSG_CHECK_ARG(a->impl == 0 || (a->impl >= 2 && a->impl <= 4), "dsg_conv: bad impl %d", a->impl);
   if (a->out_nchw_f32) {
     DSG_CHECK_ARG(a->mode == 0 && a->cout == 16 && a->cout_real >= 1 && a->cout_real <= 16 && !a->residual &&
                       !a->csc1 && a->impl != 2 && (uintptr_t)a->out_nchw_f32 % 4 == 0,
                   "dsg_conv: conv_out form needs mode 0, cout 16, 1 <= cout_real <= 16, no residual/shortcut");
-    rc = launch_halo_conv(a, 16, st);
+    rc = launch_halo_conv(a, 16, 0, st);
     if (rc == DSG_HALO_SKIP) { set_error("dsg_conv: conv_out form needs W >= 8 and H >= 18"); return DSG_ERR_UNSUPPORTED; }
     return rc;
   }
@@ -453,9 +453,9 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
   DSG_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && a->cout % bn == 0, "dsg_conv: bad block_n %d for cout %d", bn,
                 a->cout);
   if (a->impl != 2) {
-    rc = launch_halo_conv(a, bn, st);
+    rc = launch_halo_conv(a, bn, a->impl == 4 ? 1 : 0, st);
     if (rc != DSG_HALO_SKIP) return rc;
-    if (a->impl == 3) { set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel"); return DSG_ERR_UNSUPPORTED; }
+    if (a->impl >= 3) { set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel"); return DSG_ERR_UNSUPPORTED; }
   }
   switch (bn) {
     case 64: return launch_igemm<64>(p, st);

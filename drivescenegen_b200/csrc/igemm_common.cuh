@@ -203,6 +203,6 @@ inline IgSrc dense_src(const void* ptr, int C, int H, int W) {
 
 // igemm_halo.cu: returns DSG_OK, an error, or DSG_HALO_SKIP when the shape is outside what the halo kernel covers
 constexpr int DSG_HALO_SKIP = 1;
-int launch_halo_conv(const dsg_conv_args* a, int block_n, cudaStream_t st);
+int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStream_t st);
 
 }  // namespace dsg

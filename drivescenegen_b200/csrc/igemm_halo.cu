@@ -58,12 +58,18 @@ struct alignas(64) HlMaps {
   CUtensorMap b;
 };
 
-template <int BLOCK_N, int MT>
+// CG = CTAs per MMA: 1, or 2 for tcgen05 cta_group::2 — a cluster of two CTAs shares every MMA (M = 256): each CTA
+// feeds its own 128 pixel rows of A but only HALF of the weight tile, which halves the per-SM shared-memory reads of
+// B.  The UMMA operand fetch tops out near 76 B/clk/SM (tools/umma_probe.cu), which caps a lone CTA at 76 % / 60 %
+// of the tensor peak for N = 256 / 128; the CTA pair lifts that to ~100 % / 80 %.
+template <int BLOCK_N, int MT, int CG>
 struct HlCfg {
   static constexpr int A_SLOT = MT * 16384 + 4096;  // (MT*8 + 2) rows x 16 px x 128 B (the TW = 8 box is smaller)
-  static constexpr int B_SLOT = BLOCK_N * 128;
+  static constexpr int B_ROWS = BLOCK_N / CG;       // weight rows this CTA loads per tap
+  static constexpr int B_SLOT = B_ROWS * 128;
   static constexpr int NA = BLOCK_N == 128 ? 3 : 4;
-  static constexpr int NB = BLOCK_N == 16 ? 12 : (BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4));
+  static constexpr int NB = CG == 2 ? (BLOCK_N == 256 ? 8 : 12)
+                                    : (BLOCK_N == 16 ? 12 : (BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4)));
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
   static constexpr int SMEM_BYTES =
@@ -76,7 +82,8 @@ struct HlCfg {
 struct HlTile {
   int n, h0, w0, nb, pa, pb;
 };
-__device__ __forceinline__ HlTile hl_decode(const HlPlan& p, int64_t t) {
+// cg CTAs of a cluster share tile t: CTA `rank` takes rows [rank * TH, (rank + 1) * TH) of the cg * TH tall tile
+__device__ __forceinline__ HlTile hl_decode(const HlPlan& p, int64_t t, int cg = 1, int rank = 0) {
   HlTile c;
   c.nb = (int)(t % p.n_blocks); t /= p.n_blocks;
   const int tw = (int)(t % p.tiles_w); t /= p.tiles_w;
@@ -84,18 +91,86 @@ __device__ __forceinline__ HlTile hl_decode(const HlPlan& p, int64_t t) {
   c.n = (int)(t % p.N);
   const int phase = (int)(t / p.N);
   c.pa = phase >> 1; c.pb = phase & 1;
-  c.h0 = th * p.TH; c.w0 = tw * p.TW;
+  c.h0 = (th * cg + rank) * p.TH; c.w0 = tw * p.TW;
   return c;
+}
+
+// ---- cluster / cta_group::2 PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a location in this CTA's shared memory) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_holder) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int CG>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ HlPlan p) {
-  using Cfg = HlCfg<BLOCK_N, MT>;
+  using Cfg = HlCfg<BLOCK_N, MT, CG>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,15 +196,24 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     for (int i = 0; i < HL_MAX_MAPS; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
   }
+  // CTA pair (CG = 2): rank 0 is the leader — it owns the "full" barriers (both producers report to them), issues
+  // every MMA and collects both epilogues' "accumulator drained" arrivals; "empty"/"accumulator full" barriers
+  // exist in both CTAs and are signalled together by multicast commits.
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int64_t tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], CG); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_holder);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_holder);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
 
@@ -137,25 +221,38 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
     {
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
-      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const HlTile tc = hl_decode(p, t);
-        const int brow = (tc.pa * 2 + tc.pb) * p.cout + tc.nb * BLOCK_N;
+      for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
+        const HlTile tc = hl_decode(p, t, CG, (int)rank);
+        // a CTA pair splits the weight tile: this CTA loads rows [rank * B_ROWS, (rank + 1) * B_ROWS) of it
+        const int brow = (tc.pa * 2 + tc.pb) * p.cout + tc.nb * BLOCK_N + (int)rank * Cfg::B_ROWS;
         for (int g = 0; g < p.ngroups; ++g) {
           const HlGroup& G = p.grp[g];
           const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
           for (int c = 0; c < G.nchunks; ++c) {
             mbar_wait(&a_empty[as], aph ^ 1);
             if (elect_one_sync()) {
-              mbar_arrive_expect_tx(&a_full[as], (uint32_t)G.bytes);
-              tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_full[as], c * IG_BLOCK_K, wx, hy, tc.n);
+              if constexpr (CG == 2) {
+                const uint32_t fb = mapa_u32(&a_full[as], 0);
+                mbar_arrive_expect_tx_cluster(fb, (uint32_t)G.bytes);
+                tma_load_4d_cg2(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], fb, c * IG_BLOCK_K, wx, hy, tc.n);
+              } else {
+                mbar_arrive_expect_tx(&a_full[as], (uint32_t)G.bytes);
+                tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_full[as], c * IG_BLOCK_K, wx, hy, tc.n);
+              }
             }
             __syncwarp();
             if (++as == NA) { as = 0; aph ^= 1; }
             for (int tp = 0; tp < G.ntaps; ++tp) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               if (elect_one_sync()) {
-                mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
-                tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+                if constexpr (CG == 2) {
+                  const uint32_t fb = mapa_u32(&b_full[bs], 0);
+                  mbar_arrive_expect_tx_cluster(fb, (uint32_t)Cfg::B_SLOT);
+                  tma_load_2d_cg2(b_ring + bs * Cfg::B_SLOT, &maps.b, fb, (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+                } else {
+                  mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
+                  tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+                }
               }
               __syncwarp();
               if (++bs == NB) { bs = 0; bph ^= 1; }
@@ -166,11 +263,12 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (warp-uniform loop, elected lane issues)
-    {
-      const uint32_t idesc = umma_idesc_f16(BLOCK_N);
+    if (rank == 0) {
+      // instruction descriptor: M = 128 per CTA, i.e. 256 for the pair
+      const uint32_t idesc = (umma_idesc_f16(BLOCK_N) & ~(0x1Fu << 24)) | ((uint32_t)((128 * CG) >> 4) << 24);
       int as = 0, bs = 0; uint32_t aph = 0, bph = 0;
       int acc = 0; uint32_t acc_ph = 0;
-      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
         mbar_wait(&tempty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BLOCK_N);
@@ -192,13 +290,24 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
                 for (int m = 0; m < MT; ++m) {
                   const uint64_t da = umma_desc_sw128(a_addr + (uint32_t)((G.row_off[tp] + m * half_rows) * row_bytes));
 #pragma unroll
-                  for (int k = 0; k < IG_BLOCK_K / 16; ++k)
-                    umma_f16(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                             k == 0 ? accum : 1u);
+                  for (int k = 0; k < IG_BLOCK_K / 16; ++k) {
+                    if constexpr (CG == 2)
+                      umma_f16_cg2(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                   idesc, k == 0 ? accum : 1u);
+                    else
+                      umma_f16(d_tmem + (uint32_t)(m * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                               k == 0 ? accum : 1u);
+                  }
                 }
-                umma_commit(&b_empty[bs]);                 // frees the weight slot when these MMAs retire
-                if (last_tap) umma_commit(&a_empty[as]);   // frees the activation box
-                if (last_of_tile) umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
+                if constexpr (CG == 2) {
+                  umma_commit_cg2(&b_empty[bs]);                   // both CTAs' weight slots
+                  if (last_tap) umma_commit_cg2(&a_empty[as]);     // both CTAs' activation boxes
+                  if (last_of_tile) umma_commit_cg2(&tfull[acc]);  // both CTAs' epilogues
+                } else {
+                  umma_commit(&b_empty[bs]);                 // frees the weight slot when these MMAs retire
+                  if (last_tap) umma_commit(&a_empty[as]);   // frees the activation box
+                  if (last_of_tile) umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
+                }
               }
               __syncwarp();
               accum = 1;
@@ -217,8 +326,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     const int te = threadIdx.x - 64;
     const int lh0 = row >> p.tw_shift, lw = row & (p.TW - 1);
     int acc = 0; uint32_t acc_ph = 0;
-    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const HlTile tc = hl_decode(p, t);
+    for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
+      const HlTile tc = hl_decode(p, t, CG, (int)rank);
       const int n0 = tc.nb * BLOCK_N;
       float* sb = sbias + acc * BLOCK_N;
       for (int j = te; j < BLOCK_N; j += 128) {
@@ -260,7 +369,10 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader issues the MMAs
+        else mbar_arrive(&tempty[acc]);
+      }
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
         continue;
       }
@@ -272,7 +384,10 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         epi_tile<BLOCK_N, MT>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader issues the MMAs
+        else mbar_arrive(&tempty[acc]);
+      }
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         epi_stats_flush<BLOCK_N>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
@@ -283,16 +398,18 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may leave while the other still signals / reads it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------ host side
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int CG>
 static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
-  using Cfg = HlCfg<BLOCK_N, MT>;
+  using Cfg = HlCfg<BLOCK_N, MT, CG>;
   HlPlan p;
   memset(&p, 0, sizeof(p));
   const int oh = a->h, ow = a->w;  // GEMM pixel grid (per phase for mode 2)
@@ -302,7 +419,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   const int halo = a->mode == 0 ? 2 : 1;
   if (oh < th + halo) return DSG_HALO_SKIP;  // keep every TMA box inside the tensor extents
   p.N = a->n; p.OH = oh; p.OW = ow; p.TW = tw; p.tw_shift = sh; p.TH = th;
-  p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th);
+  p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th * CG);  // a CTA pair stacks its two tiles vertically
   p.cout = a->cout; p.n_blocks = a->cout / BLOCK_N;
   const int cin_chunks = a->cin / 64;
   HlMaps maps;
@@ -350,7 +467,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
     }
     k_total = (int64_t)4 * a->cin;
   }
-  rc = make_map_b(&maps.b, (const __half*)a->wpacked, k_total, (int64_t)p.phases * a->cout, BLOCK_N);
+  rc = make_map_b(&maps.b, (const __half*)a->wpacked, k_total, (int64_t)p.phases * a->cout, Cfg::B_ROWS);
   if (rc) return rc;
   const int out_h = oh * p.omul, out_w = ow * p.omul;
   p.oW = a->cout; p.oH = (int64_t)out_w * a->cout; p.oN = (int64_t)out_h * out_w * a->cout;
@@ -361,24 +478,48 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT, CG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
     attr_set = true;
   }
-  const int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  igemm_halo_kernel<BLOCK_N, MT><<<(unsigned)grid, HL_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  const int64_t slots = num_sms() / CG;  // CTAs, or CTA pairs
+  const int64_t grid = (p.total_tiles < slots ? p.total_tiles : slots) * CG;
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(HL_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<BLOCK_N, MT, CG>, maps, p);
+    if (e != cudaSuccess) { set_error("igemm_halo (CTA pair): launch: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
+  } else {
+    igemm_halo_kernel<BLOCK_N, MT, CG><<<(unsigned)grid, HL_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  }
   DSG_CUDA_LAUNCH_CHECK("dsg_conv/igemm_halo");
   return DSG_OK;
 }
 
-int launch_halo_conv(const dsg_conv_args* a, int block_n, cudaStream_t st) {
+int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStream_t st) {
   if (a->mode != 0 && a->mode != 2) return DSG_HALO_SKIP;
+  if (cta_pair) {
+    switch (block_n) {
+      case 64: return launch_halo<64, 2, 2>(a, st);
+      case 128: return launch_halo<128, 2, 2>(a, st);
+      case 256: return launch_halo<256, 1, 2>(a, st);
+      default: return DSG_HALO_SKIP;
+    }
+  }
   switch (block_n) {
-    case 16: return launch_halo<16, 2>(a, st);
-    case 64: return launch_halo<64, 2>(a, st);
-    case 128: return launch_halo<128, 2>(a, st);
-    case 256: return launch_halo<256, 1>(a, st);
+    case 16: return launch_halo<16, 2, 1>(a, st);
+    case 64: return launch_halo<64, 2, 1>(a, st);
+    case 128: return launch_halo<128, 2, 1>(a, st);
+    case 256: return launch_halo<256, 1, 1>(a, st);
     default: return DSG_HALO_SKIP;
   }
 }

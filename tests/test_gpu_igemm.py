@@ -246,3 +246,56 @@ def test_conv_epilogue_groupnorm_stats(case):
     a = ops.group_norm(y, None, gamma, beta, 32, 1e-5, 1, stats1=st)
     bref = ops.group_norm(y, None, gamma, beta, 32, 1e-5, 1)
     assert (a.float() - bref.float()).abs().max().item() < 4e-3
+
+
+# the cta_group::2 form of the halo-reuse kernel (impl = 4): a cluster of two CTAs per 2 x TH x TW pixel tile
+PAIR_CASES = [
+    # mode, n, h, w, cin, cout, csc1, csc2, residual, temb, stats
+    (0, 2, 32, 32, 128, 256, 0, 0, False, True, True),      # BLOCK_N 256: 8-row tiles, pair = 16 rows
+    (0, 1, 64, 64, 256, 256, 0, 0, True, True, False),      # residual through the epilogue
+    (0, 3, 32, 32, 512, 512, 0, 0, True, False, True),      # two N blocks, long K
+    (0, 2, 64, 64, 64, 128, 0, 0, False, True, True),       # BLOCK_N 128: two accumulators per CTA, pair = 32 rows
+    (0, 1, 40, 24, 128, 128, 0, 0, True, False, True),      # ragged: second CTA's tile partly / fully outside
+    (0, 1, 64, 64, 128, 128, 64, 128, False, False, False), # shortcut panels
+    (0, 2, 64, 64, 64, 64, 64, 0, False, True, True),       # BLOCK_N 64 + identity-style shortcut panel
+    (0, 1, 256, 256, 64, 64, 0, 0, False, False, True),     # many tiles per pair (ring wrap-around)
+    (2, 1, 32, 32, 128, 128, 0, 0, False, False, True),     # sub-pixel upsample conv
+    (2, 2, 32, 32, 256, 256, 0, 0, False, False, False),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
+def test_igemm_halo_cta_pair(case):
+    from drivescenegen_b200 import ops
+    mode, n, h, w, cin, cout, csc1, csc2, use_res, use_temb, use_stats = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    d = _dev()
+    x = torch.randn(n, h, w, cin, generator=g).half()
+    fan = cin * 9 + csc1 + csc2
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / fan ** 0.5
+    b = torch.randn(cout, generator=g)
+    oh, ow = (2 * h, 2 * w) if mode == 2 else (h, w)
+    sc = []
+    if csc1:
+        sc.append(torch.randn(n, h, w, csc1, generator=g).half())
+    if csc2:
+        sc.append(torch.randn(n, h, w, csc2, generator=g).half())
+    w_sc = torch.randn(cout, csc1 + csc2, generator=g) / fan ** 0.5 if sc else None
+    res = torch.randn(n, oh, ow, cout, generator=g).half() if use_res else None
+    temb = torch.randn(n, cout + 32, generator=g) if use_temb else None
+    ref = _ref_conv(mode, x, wt, b, temb, 32 if use_temb else 0, res, sc, w_sc)
+    wp = ops.pack_conv_weight(mode, wt.to(d), None if w_sc is None else w_sc.to(d))
+    kw = dict(bias=b.to(d), temb=None if temb is None else temb.to(d), temb_off=32 if use_temb else 0,
+              residual=None if res is None else res.to(d), sc1=sc[0].to(d) if len(sc) > 0 else None,
+              sc2=sc[1].to(d) if len(sc) > 1 else None)
+    st1 = torch.zeros(n, cout, 2, dtype=torch.int64, device=d) if use_stats else None
+    st4 = torch.zeros(n, cout, 2, dtype=torch.int64, device=d) if use_stats else None
+    one = ops.conv(mode, x.to(d), wp, cout, impl=3, out_stats=st1, **kw)   # single-CTA halo kernel
+    two = ops.conv(mode, x.to(d), wp, cout, impl=4, out_stats=st4, **kw)   # CTA pair
+    torch.cuda.synchronize()
+    err = (two.float().permute(0, 3, 1, 2).cpu() - ref).abs().max().item()
+    assert err < 2e-2, f"CTA-pair kernel vs torch fp32: {err}"
+    # same tiles, same K order, same fp32 accumulation: the pair must reproduce the single-CTA kernel bit for bit
+    assert torch.equal(one, two), (one.float() - two.float()).abs().max()
+    if use_stats:
+        assert torch.equal(st1, st4)
