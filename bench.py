@@ -57,7 +57,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -236,10 +236,17 @@ def main():
     gn_bytes = sum(meta["bytes"] for n, meta, m in table if n.startswith("gn_"))
     attn_ms = sum(m for n, meta, m in table if n == "attention")
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "igemm_kernel (all conv3x3/1x1/linear launches of one step)",
+    # DRAM traffic of the same launches from the committed `ncu --set full` capture (profiles/), per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", f"conv_traffic_b{B}_{S}.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor",
+                "kernel": "igemm_halo_kernel / igemm_kernel (all conv3x3/1x1/linear launches of one step)",
                 "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tflops_sustained"], "peak_source": pk["source"] + " bf16 sustained (cuBLAS)",
-                "traffic": None, "launches": n_conv, "avg_launch_ms": conv_ms / n_conv,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r1b_ncu_full_conv.json)",
+                "launches": n_conv, "avg_launch_ms": conv_ms / n_conv,
                 "algorithmic_flops_per_step": conv_fl, "share_of_step": conv_ms / total_ms}
     breakdown = {"conv_ms": conv_ms, "groupnorm_ms": gn_ms, "groupnorm_gbs": gn_bytes / (gn_ms * 1e-3) / 1e9,
                  "attention_ms": attn_ms, "eager_step_ms": total_ms,

@@ -39,6 +39,23 @@ class ConvArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    """mirror of ``dsg_wgrad_args`` (include/dsg_b200.h)."""
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+        ("x", C.c_void_p),
+        ("dy", C.c_void_p),
+        ("grad", C.c_void_p),
+        ("ci_total", C.c_int32), ("ci_off", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("inv_scale", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+        ("impl", C.c_int32),
+    ]
+
+
 _i32, _i64, _p, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/dsg_b200.h declares (tests check this)
@@ -62,6 +79,25 @@ SIGNATURES = {
     "dsg_pack_conv_weight": (C.c_int, [_i32, _p, _i32, _i32, _p, _i32, _p, _p]),
     "dsg_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dsg_attention_ex": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p]),
+    # ---- training path
+    "dsg_packed_k_dgrad": (_i64, [_i32, _i32]),
+    "dsg_packed_rows_dgrad": (_i64, [_i32, _i32]),
+    "dsg_grad_scale": (C.c_int, [_p, _i64, _p, _i32, _p, _p]),
+    "dsg_time_embed_ex": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p, _p]),
+    "dsg_lin_dgrad_small": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
+    "dsg_lin_wgrad_small": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "dsg_gn_bwd": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _p,
+                             _i32, _i32, _i64, _i32, _p]),
+    "dsg_gn_bwd_params": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p]),
+    "dsg_colsum_h16": (C.c_int, [_p, _i64, _i32, _p, _i32, _p]),
+    "dsg_colsum_finalize": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p]),
+    "dsg_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
+    "dsg_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "dsg_conv_out_dgrad_weight": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
+    "dsg_small_wgrad": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
+    "dsg_attention_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dsg_grad_norm": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _p, _p]),
+    "dsg_adamw_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i32, _p, _p]),
 }
 
 _lib = None

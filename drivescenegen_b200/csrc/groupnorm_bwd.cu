@@ -1,0 +1,391 @@
+// groupnorm_bwd.cu — backward of GroupNorm(+SiLU) over NHWC fp16 activations (training path).
+// Replaces the autograd backward of torch.nn.GroupNorm(32, C, eps) + SiLU inside upstream ResnetBlock2D / Attention /
+// conv_norm_out (diffusers 0.20.0 models/resnet.py; reached from DriveSceneGen/pipeline/training_pipeline.py:86
+// `accelerator.backward(loss)`), including the split of the gradient over the two tensors that torch.cat joined.
+//
+// With xh = (x - mean_g) * rstd_g, y = gamma * xh + beta, a = act(y) and the incoming gradient da:
+//   g        = da * act'(y)
+//   A_c      = sum_px g            (= d beta_c per sample)       B_c = sum_px g * xh   (= d gamma_c per sample)
+//   m1_g     = sum_{c in g} gamma_c A_c / count                  m2_g = sum_{c in g} gamma_c B_c / count
+//   dx       = rstd_g * (gamma_c * g - m1_g - xh * m2_g)
+// Two streaming passes: gn_bwd_stats_kernel (reads da, x) writes per-(sample, pixel-chunk, channel) partials of A and B
+// in a fixed layout; gn_bwd_apply_kernel (reads da, x again) sums the chunk partials in a fixed order — deterministic,
+// no atomics — and writes dx, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
+// content of the destination: a tensor with two consumers), split over the two concatenated sources.  It can also emit
+// per-CTA column sums of what it wrote (the time-embedding / conv1-bias gradient of a ResnetBlock).
+// Forward statistics come from the same int64 per-channel totals the forward used (groupnorm.cu).
+#include "common.cuh"
+
+namespace dsg {
+
+constexpr int GB_THREADS = 256;
+constexpr int GB_MAX_GROUPS = 64;
+constexpr int GB_MAX_C = 2048;
+constexpr int GB_MAX_CHUNKS = 64;
+
+struct GnBwdArgs {
+  const __half* dy;   // [n][hw][C] incoming gradient (w.r.t. the activated, normalised tensor)
+  const __half* x1; int c1; const long long* st1;
+  const __half* x2; int c2; const long long* st2;
+  const float* gamma; const float* beta;
+  float eps; int act;
+  float* partial;     // [n][chunks][C][2]
+  int chunks;
+  const __half* addend;  // optional [n][hw][C]
+  __half* dx1; int acc1;
+  __half* dx2; int acc2;
+  float* colsum;      // optional [n][ctas][C]
+  int64_t hw; int groups;
+  int64_t px_per_block;
+};
+
+// mean / rstd per group from the exact integer totals (same arithmetic as gn_apply_kernel)
+__device__ __forceinline__ void gn_moments(const GnBwdArgs& a, int n, float* s_mean, float* s_rstd,
+                                           unsigned long long (*s_t)[2]) {
+  const int C = a.c1 + a.c2, cpg = C / a.groups;
+  if ((int)threadIdx.x < a.groups) { s_t[threadIdx.x][0] = 0ull; s_t[threadIdx.x][1] = 0ull; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+    const longlong2 tv = *reinterpret_cast<const longlong2*>(
+        c < a.c1 ? a.st1 + ((int64_t)n * a.c1 + c) * 2 : a.st2 + ((int64_t)n * a.c2 + (c - a.c1)) * 2);
+    if (tv.x != 0 || tv.y != 0) {
+      atomicAdd(&s_t[c / cpg][0], (unsigned long long)tv.x);
+      atomicAdd(&s_t[c / cpg][1], (unsigned long long)tv.y);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < a.groups) {
+    const int g = threadIdx.x;
+    const double inv_cnt = 1.0 / ((double)a.hw * (double)cpg);
+    const double mg = (double)(long long)s_t[g][0] * (1.0 / 16777216.0) * inv_cnt;
+    double vg = (double)(long long)s_t[g][1] * (1.0 / 1048576.0) * inv_cnt - mg * mg;
+    if (vg < 0.0) vg = 0.0;
+    s_mean[g] = (float)mg;
+    s_rstd[g] = (float)(1.0 / sqrt(vg + (double)a.eps));
+  }
+  __syncthreads();
+}
+
+// d/dy [y * sigmoid(y)]
+__device__ __forceinline__ float silu_grad_f(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  const float sg = fmaf(0.5f, t, 0.5f);
+  return sg * fmaf(y, 1.0f - sg, 1.0f);
+}
+
+__global__ void __launch_bounds__(GB_THREADS) gn_bwd_stats_kernel(const GnBwdArgs a) {
+  const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
+  const int ppi = GB_THREADS / V;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS];
+  __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
+  __shared__ float s_part[2][GB_THREADS * 8];
+  gn_moments(a, n, s_mean, s_rstd, s_t);
+  const bool active = (int)threadIdx.x < ppi * V;
+  if (active) {
+    const int v = threadIdx.x % V, prow = threadIdx.x / V;
+    const int ch0 = v << 3;
+    const bool from1 = ch0 < a.c1;
+    const __half* src = from1 ? a.x1 : a.x2;
+    const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
+    float ga[8], yb[8], mu[8], rs[8], sA[8], sB[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = ch0 + j, g = ch / cpg;
+      mu[j] = s_mean[g]; rs[j] = s_rstd[g];
+      ga[j] = a.gamma[ch] * rs[j];
+      yb[j] = a.beta[ch] - mu[j] * ga[j];
+      sA[j] = 0.f; sB[j] = 0.f;
+    }
+    const int64_t base_px = (int64_t)n * a.hw;
+    const int64_t p_begin = (int64_t)chunk * a.px_per_block;
+    int64_t p_end = p_begin + a.px_per_block;
+    if (p_end > a.hw) p_end = a.hw;
+    for (int64_t p = p_begin + prow; p < p_end; p += 2 * ppi) {
+      const int64_t p2 = p + ppi;
+      const bool has2 = p2 < p_end;
+      const uint4 rx0 = ldg_nc_v4(src + (base_px + p) * cs + co);
+      const uint4 rd0 = ldg_nc_v4(a.dy + (base_px + p) * C + ch0);
+      uint4 rx1 = rx0, rd1 = rd0;
+      if (has2) {
+        rx1 = ldg_nc_v4(src + (base_px + p2) * cs + co);
+        rd1 = ldg_nc_v4(a.dy + (base_px + p2) * C + ch0);
+      }
+      float fx[8], fd[8];
+      unpack8(rx0, fx); unpack8(rd0, fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
+        sA[j] += g;
+        sB[j] = fmaf(g, (fx[j] - mu[j]) * rs[j], sB[j]);
+      }
+      if (has2) {
+        unpack8(rx1, fx); unpack8(rd1, fd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
+          sA[j] += g;
+          sB[j] = fmaf(g, (fx[j] - mu[j]) * rs[j], sB[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[0][prow * C + ch0 + j] = sA[j];
+      s_part[1][prow * C + ch0 + j] = sB[j];
+    }
+  }
+  __syncthreads();
+  float* o = a.partial + ((int64_t)n * a.chunks + chunk) * C * 2;
+  for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+    float tA = 0.f, tB = 0.f;
+    for (int r = 0; r < ppi; ++r) {  // fixed order
+      tA += s_part[0][r * C + c];
+      tB += s_part[1][r * C + c];
+    }
+    reinterpret_cast<float2*>(o)[c] = make_float2(tA, tB);
+  }
+}
+
+__global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+  const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
+  const int ppi = GB_THREADS / V;
+  const int n = blockIdx.y;
+  __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS], s_m1[GB_MAX_GROUPS], s_m2[GB_MAX_GROUPS];
+  __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
+  __shared__ float s_part[2][GB_THREADS * 8];  // prologue: gamma * A / gamma * B per channel; epilogue: column sums
+  gn_moments(a, n, s_mean, s_rstd, s_t);
+  {
+    const float* pp = a.partial + (int64_t)n * a.chunks * C * 2;
+    for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+      float tA = 0.f, tB = 0.f;
+      for (int k = 0; k < a.chunks; ++k) {  // fixed order
+        const float2 v = reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2)[c];
+        tA += v.x; tB += v.y;
+      }
+      const float gm = a.gamma[c];
+      s_part[0][c] = gm * tA;
+      s_part[1][c] = gm * tB;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < a.groups) {
+      const int g = threadIdx.x;
+      float m1 = 0.f, m2 = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { m1 += s_part[0][c]; m2 += s_part[1][c]; }
+      const float inv_cnt = (float)(1.0 / ((double)a.hw * (double)cpg));
+      s_m1[g] = m1 * inv_cnt;
+      s_m2[g] = m2 * inv_cnt;
+    }
+    __syncthreads();
+  }
+  const bool active = (int)threadIdx.x < ppi * V;
+  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  const int ch0 = v << 3;
+  float cs_acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs_acc[j] = 0.f;
+  if (active) {
+    const bool from1 = ch0 < a.c1;
+    const __half* src = from1 ? a.x1 : a.x2;
+    __half* dst = from1 ? a.dx1 : a.dx2;
+    const int accum = from1 ? a.acc1 : a.acc2;
+    const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
+    float ga[8], yb[8], mu[8], rs[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = ch0 + j, g = ch / cpg;
+      mu[j] = s_mean[g]; rs[j] = s_rstd[g];
+      ga[j] = a.gamma[ch] * rs[j];
+      yb[j] = a.beta[ch] - mu[j] * ga[j];
+      k1[j] = rs[j] * s_m1[g];
+      k2[j] = rs[j] * s_m2[g];
+    }
+    const int64_t base_px = (int64_t)n * a.hw;
+    const int64_t p_begin = (int64_t)blockIdx.x * a.px_per_block;
+    int64_t p_end = p_begin + a.px_per_block;
+    if (p_end > a.hw) p_end = a.hw;
+    for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
+      const uint4 rx = ldg_nc_v4(src + (base_px + p) * cs + co);
+      const uint4 rd = ldg_nc_v4(a.dy + (base_px + p) * C + ch0);
+      uint4 ra = make_uint4(0, 0, 0, 0), ro = make_uint4(0, 0, 0, 0);
+      if (a.addend) ra = ldg_nc_v4(a.addend + (base_px + p) * C + ch0);
+      if (accum) ro = *reinterpret_cast<const uint4*>(dst + (base_px + p) * cs + co);
+      float fx[8], fd[8], fa[8], fo[8], r[8];
+      unpack8(rx, fx); unpack8(rd, fd); unpack8(ra, fa); unpack8(ro, fo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
+        const float xh = (fx[j] - mu[j]) * rs[j];
+        float d = fmaf(ga[j], g, -k1[j]);
+        d = fmaf(-xh, k2[j], d);
+        cs_acc[j] += d;
+        r[j] = (d + fa[j]) + fo[j];
+      }
+      stg_v4(dst + (base_px + p) * cs + co, pack8(r));
+    }
+  }
+  if (a.colsum) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_part[0][prow * C + ch0 + j] = cs_acc[j];
+    }
+    __syncthreads();
+    float* o = a.colsum + ((int64_t)n * gridDim.x + blockIdx.x) * C;
+    for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+      float t = 0.f;
+      for (int r = 0; r < ppi; ++r) t += s_part[0][r * C + c];
+      o[c] = t;
+    }
+  }
+}
+
+// d gamma / d beta: sum the per-(sample, chunk) partials in a fixed order, scale, store
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ partial, int rows, int C,
+                                                            const float* __restrict__ inv_scale,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tA = 0.f, tB = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float2 v = reinterpret_cast<const float2*>(partial + (int64_t)r * C * 2)[c];
+    tA += v.x; tB += v.y;
+  }
+  const float s = inv_scale ? *inv_scale : 1.0f;
+  dbeta[c] = tA * s;
+  dgamma[c] = tB * s;
+}
+
+// column sums of an fp16 [rows][C] tensor: per-block partials [blocks][C] (fp32), fixed order inside a block
+__global__ void __launch_bounds__(GB_THREADS) colsum_h16_kernel(const __half* __restrict__ x, int64_t rows, int C,
+                                                                float* __restrict__ partial, int64_t rows_per_block) {
+  const int V = C >> 3, ppi = GB_THREADS / V;
+  __shared__ float s_part[GB_THREADS * 8];
+  const bool active = (int)threadIdx.x < ppi * V;
+  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  if (active) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    for (int64_t r = r0 + prow; r < r1; r += 2 * ppi) {
+      const uint4 a0 = ldg_nc_v4(x + r * C + (v << 3));
+      uint4 a1 = make_uint4(0, 0, 0, 0);
+      if (r + ppi < r1) a1 = ldg_nc_v4(x + (r + ppi) * C + (v << 3));
+      float f0[8], f1[8];
+      unpack8(a0, f0); unpack8(a1, f1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f0[j] + f1[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[prow * C + (v << 3) + j] = s[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+    float t = 0.f;
+    for (int r = 0; r < ppi; ++r) t += s_part[r * C + c];
+    partial[(int64_t)blockIdx.x * C + c] = t;
+  }
+}
+
+// partial [n][parts][C] -> per_n [n][per_n_stride] (+ per_n_off, raw) and total[c] = scale * sum over n and parts
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int n, int parts,
+                                                              int C, float* __restrict__ per_n, int per_n_stride,
+                                                              int per_n_off, const float* __restrict__ inv_scale,
+                                                              float* __restrict__ total, float* __restrict__ total2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tot = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    for (int k = 0; k < parts; ++k) t += partial[((int64_t)i * parts + k) * C + c];
+    if (per_n) per_n[(int64_t)i * per_n_stride + per_n_off + c] = t;
+    tot += t;
+  }
+  const float s = inv_scale ? *inv_scale : 1.0f;
+  if (total) total[c] = tot * s;
+  if (total2) total2[c] = tot * s;
+}
+
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" {
+
+int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
+               const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
+               int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
+               int32_t colsum_parts, int32_t n, int64_t hw, int32_t groups, void* stream) {
+  DSG_CHECK_ARG(dy && x1 && stats1 && dx1 && c1 > 0 && c1 % 8 == 0, "dsg_gn_bwd: dy/x1/stats1/dx1 null or bad c1");
+  DSG_CHECK_ARG((x2 == nullptr) == (c2 == 0) && (x2 == nullptr) == (stats2 == nullptr) &&
+                    (x2 == nullptr) == (dx2 == nullptr) && c2 % 8 == 0,
+                "dsg_gn_bwd: x2/stats2/dx2/c2 mismatch");
+  const int C = c1 + c2;
+  DSG_CHECK_ARG(groups > 0 && groups <= GB_MAX_GROUPS && C % groups == 0 && C <= GB_MAX_C,
+                "dsg_gn_bwd: bad groups %d for C=%d", groups, C);
+  DSG_CHECK_ARG(gamma && beta && partial && chunks >= 1 && chunks <= GB_MAX_CHUNKS, "dsg_gn_bwd: bad partial/chunks");
+  DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_bwd: bad n/hw");
+  DSG_CHECK_ARG((colsum == nullptr) == (colsum_parts == 0) && colsum_parts >= 0 && colsum_parts <= 65535,
+                "dsg_gn_bwd: colsum/colsum_parts mismatch");
+  DSG_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)dx1 | (uintptr_t)dx2 |
+                  (uintptr_t)addend | (uintptr_t)stats1 | (uintptr_t)stats2) % 16) == 0 && (uintptr_t)partial % 8 == 0,
+                "dsg_gn_bwd: unaligned pointer");
+  if (n == 0) return DSG_OK;
+  GnBwdArgs a;
+  a.dy = (const __half*)dy;
+  a.x1 = (const __half*)x1; a.c1 = c1; a.st1 = (const long long*)stats1;
+  a.x2 = (const __half*)x2; a.c2 = c2; a.st2 = (const long long*)stats2;
+  a.gamma = gamma; a.beta = beta; a.eps = eps; a.act = act;
+  a.partial = partial; a.chunks = chunks;
+  a.addend = (const __half*)addend;
+  a.dx1 = (__half*)dx1; a.acc1 = acc1; a.dx2 = (__half*)dx2; a.acc2 = acc2;
+  a.colsum = colsum; a.hw = hw; a.groups = groups;
+  cudaStream_t st = (cudaStream_t)stream;
+  a.px_per_block = ceil_div64(hw, chunks);
+  gn_bwd_stats_kernel<<<dim3((unsigned)chunks, n), GB_THREADS, 0, st>>>(a);
+  DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
+  int64_t ctas = colsum_parts;
+  if (ctas == 0) {
+    ctas = (148 * 4) / n;
+    if (ctas < 1) ctas = 1;
+    const int64_t max_ctas = ceil_div64(hw, 32);
+    if (ctas > max_ctas) ctas = max_ctas;
+  }
+  a.px_per_block = ceil_div64(hw, ctas);
+  gn_bwd_apply_kernel<<<dim3((unsigned)ctas, n), GB_THREADS, 0, st>>>(a);
+  DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/apply");
+  return DSG_OK;
+}
+
+int dsg_gn_bwd_params(const float* partial, int32_t rows, int32_t c, const float* inv_scale, float* dgamma,
+                      float* dbeta, void* stream) {
+  DSG_CHECK_ARG(partial && dgamma && dbeta && rows >= 0 && c > 0, "dsg_gn_bwd_params: bad args");
+  gn_bwd_params_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, rows, c, inv_scale, dgamma, dbeta);
+  DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd_params");
+  return DSG_OK;
+}
+
+int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32_t parts, void* stream) {
+  DSG_CHECK_ARG(x && partial && rows >= 0 && c > 0 && c % 8 == 0 && c <= GB_MAX_C && parts >= 1,
+                "dsg_colsum_h16: bad args");
+  DSG_CHECK_ARG((uintptr_t)x % 16 == 0, "dsg_colsum_h16: unaligned pointer");
+  const int64_t rpb = ceil_div64(rows > 0 ? rows : 1, parts);
+  colsum_h16_kernel<<<parts, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)x, rows, c, partial, rpb);
+  DSG_CUDA_LAUNCH_CHECK("dsg_colsum_h16");
+  return DSG_OK;
+}
+
+int dsg_colsum_finalize(const float* partial, int32_t n, int32_t parts, int32_t c, float* per_n, int32_t per_n_stride,
+                        int32_t per_n_off, const float* inv_scale, float* total, float* total2, void* stream) {
+  DSG_CHECK_ARG(partial && n >= 0 && parts >= 1 && c > 0, "dsg_colsum_finalize: bad args");
+  colsum_finalize_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, n, parts, c, per_n,
+                                                                            per_n_stride, per_n_off, inv_scale, total,
+                                                                            total2);
+  DSG_CUDA_LAUNCH_CHECK("dsg_colsum_finalize");
+  return DSG_OK;
+}
+}

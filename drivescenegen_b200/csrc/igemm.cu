@@ -16,7 +16,7 @@
 namespace dsg {
 
 constexpr int IG_THREADS = 192;
-constexpr int IG_MAX_TAPS = 12;
+constexpr int IG_MAX_TAPS = 16;
 constexpr int IG_A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 2;  // 16 KB
 
 struct IgTap {
@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(256) igemm_naive_kernel(const __grid_constant_
 // mode 2  : row (a*2+b)*cout + co, k = (i*2+j)*cin + ci, weight = sum of the 3x3 taps that land on source
 //           offset (i + a - 1, j + b - 1) after nearest-2x upsampling
 // mode 3  : row co, k = ci (w is [cout][cin])
+// modes 10-13: the data-gradient ("dgrad") forms of modes 0-3 — the same fp32 OIHW weight, packed so that the
+//           gradient w.r.t. the conv INPUT is itself a dsg_conv over the output gradient (cout/cin below are the
+//           FORWARD conv's): 10 -> run as mode 0, 11 -> run as mode 2, 12 -> run as mode 4, 13 -> run as mode 3
 __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float* __restrict__ w, int cout, int cin,
                                                           const float* __restrict__ wsc, int csc,
                                                           __half* __restrict__ out, int64_t k_total, int64_t rows) {
@@ -280,8 +283,31 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float*
           v += w[(((int64_t)co * cin + ci) * 3 + ky) * 3 + kx];
         }
       }
-    } else {
+    } else if (mode == 3) {
       v = w[r * cin + k];
+    } else if (mode == 10) {  // dgrad of mode 0: row ci, k = (ky'*3+kx')*cout + co, spatially flipped taps
+      const int tap = (int)(k / cout), co = (int)(k - (int64_t)tap * cout);
+      v = w[(((int64_t)co * cin + r) * 3 + (2 - tap / 3)) * 3 + (2 - tap % 3)];
+    } else if (mode == 11) {  // dgrad of mode 1 (stride 2), run as a mode-2 conv over dY: row (pa*2+pb)*cin + ci
+      const int phase = (int)(r / cin), ci = (int)(r - (int64_t)phase * cin);
+      const int pa = phase >> 1, pb = phase & 1;
+      const int tap = (int)(k / cout), co = (int)(k - (int64_t)tap * cout);
+      const int ky = 3 - 2 * (tap >> 1) - pa, kx = 3 - 2 * (tap & 1) - pb;
+      if (ky >= 0 && ky < 3 && kx >= 0 && kx < 3) v = w[(((int64_t)co * cin + ci) * 3 + ky) * 3 + kx];
+    } else if (mode == 12) {  // dgrad of mode 2 (upsample conv), run as a mode-4 conv: k = ((a*2+b)*4 + i*2+j)*cout + co
+      const int e = (int)(k / cout), co = (int)(k - (int64_t)e * cout);
+      const int a = e >> 3, b = (e >> 2) & 1, ti = (e >> 1) & 1, tj = e & 1;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int oy = (a + ky - 1) >= 0 ? (a + ky - 1) / 2 : -1;
+        if (oy != ti + a - 1) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ox = (b + kx - 1) >= 0 ? (b + kx - 1) / 2 : -1;
+          if (ox != tj + b - 1) continue;
+          v += w[(((int64_t)co * cin + r) * 3 + ky) * 3 + kx];
+        }
+      }
+    } else {  // mode 13: dgrad of mode 3 (transpose)
+      v = w[k * cin + r];
     }
     out[i] = __float2half_rn(v);
   }
@@ -289,7 +315,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float*
 
 static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   memset(&p, 0, sizeof(p));
-  DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 3, "dsg_conv: bad mode %d", a->mode);
+  DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 4, "dsg_conv: bad mode %d", a->mode);
   DSG_CHECK_ARG(a->n >= 0 && a->h > 0 && a->w > 0, "dsg_conv: bad shape");
   DSG_CHECK_ARG(a->n == 0 || (a->x && a->wpacked && (a->out || a->out_nchw_f32)), "dsg_conv: null x/wpacked/out");
   DSG_CHECK_ARG(a->cin > 0 && a->cin % 64 == 0 && a->cout > 0 && (a->cout % 64 == 0 || a->out_nchw_f32),
@@ -341,6 +367,24 @@ static int build_plan(const dsg_conv_args* a, IgPlan& p) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx)
         p.taps[p.ntaps++] = IgTap{par[ky] * 2 + par[kx], sh[ky], sh[kx], cin_chunks};
+  } else if (a->mode == 4) {
+    // adjoint of mode 2 (nearest-2x upsample + 3x3): a 4x4 stride-2 gather over the four parity views of the
+    // high-resolution gradient, weights = the sub-pixel phase weights (pack mode 12)
+    DSG_CHECK_ARG(a->h % 2 == 0 && a->w % 2 == 0, "dsg_conv: mode 4 needs even H, W");
+    oh = a->h / 2; ow = a->w / 2;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        IgSrc s;
+        s.ptr = (const __half*)a->x + ((int64_t)ph * a->w + pw) * a->cin;
+        s.C = a->cin; s.H = oh; s.W = ow;
+        s.sW = 2 * (int64_t)a->cin; s.sH = 2 * (int64_t)a->w * a->cin; s.sN = (int64_t)a->h * a->w * a->cin;
+        p.src[ph * 2 + pw] = s;
+      }
+    p.nsrc = 4;
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb)
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 2; ++j) p.taps[p.ntaps++] = IgTap{pa * 2 + pb, -(i + pa - 1), -(j + pb - 1), cin_chunks};
   } else {  // mode 2
     p.src[0] = dense_src(a->x, a->cin, a->h, a->w);
     p.nsrc = 1; p.phases = 4; p.omul = 2;
@@ -408,12 +452,25 @@ int64_t dsg_packed_k(int32_t mode, int32_t cin, int32_t csc) {
   }
 }
 int64_t dsg_packed_rows(int32_t mode, int32_t cout) { return mode == 2 ? (int64_t)4 * cout : cout; }
+/* dgrad packings (pack modes 10-13): K / rows from the FORWARD conv's cin, cout */
+int64_t dsg_packed_k_dgrad(int32_t fwd_mode, int32_t cout) {
+  switch (fwd_mode) {
+    case 0: return (int64_t)9 * cout;
+    case 1: return (int64_t)4 * cout;
+    case 2: return (int64_t)16 * cout;
+    case 3: return cout;
+    default: return -1;
+  }
+}
+int64_t dsg_packed_rows_dgrad(int32_t fwd_mode, int32_t cin) { return fwd_mode == 1 ? (int64_t)4 * cin : cin; }
 
 int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_t cin, const float* w_sc,
                          int32_t csc, void* wpacked, void* stream) {
-  DSG_CHECK_ARG(mode >= 0 && mode <= 3 && w_oihw && wpacked && cout > 0 && cin > 0, "dsg_pack_conv_weight: bad args");
+  DSG_CHECK_ARG(((mode >= 0 && mode <= 3) || (mode >= 10 && mode <= 13)) && w_oihw && wpacked && cout > 0 && cin > 0,
+                "dsg_pack_conv_weight: bad args");
   DSG_CHECK_ARG((csc > 0) == (w_sc != nullptr) && (csc == 0 || mode == 0), "dsg_pack_conv_weight: shortcut mismatch");
-  const int64_t k_total = dsg_packed_k(mode, cin, csc), rows = dsg_packed_rows(mode, cout);
+  const int64_t k_total = mode >= 10 ? dsg_packed_k_dgrad(mode - 10, cout) : dsg_packed_k(mode, cin, csc);
+  const int64_t rows = mode >= 10 ? dsg_packed_rows_dgrad(mode - 10, cin) : dsg_packed_rows(mode, cout);
   int64_t blocks = ceil_div64(rows * k_total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weight_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mode, w_oihw, cout, cin, w_sc, csc,
@@ -453,8 +510,16 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
   DSG_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && a->cout % bn == 0, "dsg_conv: bad block_n %d for cout %d", bn,
                 a->cout);
   if (a->impl != 2) {
-    rc = launch_halo_conv(a, bn, a->impl == 4 ? 1 : 0, st);
-    if (rc != DSG_HALO_SKIP) return rc;
+    // default order: CTA-pair halo kernel (fastest everywhere it applies, bit-identical to the single-CTA form),
+    // then the single-CTA halo kernel, then the tap-streaming kernel
+    if (a->impl == 0 || a->impl == 4) {
+      rc = launch_halo_conv(a, bn, 1, st);
+      if (rc != DSG_HALO_SKIP) return rc;
+    }
+    if (a->impl != 4) {
+      rc = launch_halo_conv(a, bn, 0, st);
+      if (rc != DSG_HALO_SKIP) return rc;
+    }
     if (a->impl >= 3) { set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel"); return DSG_ERR_UNSUPPORTED; }
   }
   switch (bn) {

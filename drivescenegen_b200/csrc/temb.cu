@@ -14,7 +14,9 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
                                                               const float* __restrict__ freqs, int half, int flip,
                                                               const float* __restrict__ w1t, const float* __restrict__ b1,
                                                               const float* __restrict__ w2t, const float* __restrict__ b2,
-                                                              int hidden, float* __restrict__ emb_ws) {
+                                                              int hidden, float* __restrict__ emb_ws,
+                                                              float* __restrict__ saved) {
+  // saved (training only, may be NULL): per sample [ sinusoid (2*half) | pre1 | SiLU(pre1) | pre2 ] (hidden each)
   extern __shared__ float sm[];
   float* e = sm;               // [2*half]
   float* h1 = sm + 2 * half;   // [hidden]
@@ -28,6 +30,9 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     e[flip ? i : half + i] = c;
   }
   __syncthreads();
+  float* sv = saved ? saved + (int64_t)b * (in_dim + 3 * hidden) : nullptr;
+  if (sv)
+    for (int i = threadIdx.x; i < in_dim; i += blockDim.x) sv[i] = e[i];
   for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int k = 0;
@@ -38,6 +43,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     for (; k < in_dim; ++k) acc[0] = fmaf(w1t[(int64_t)k * hidden + r], e[k], acc[0]);
     const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b1[r];
     h1[r] = y / (1.0f + expf(-y));
+    if (sv) { sv[in_dim + r] = y; sv[in_dim + hidden + r] = h1[r]; }
   }
   __syncthreads();
   for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
@@ -50,6 +56,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     for (; k < hidden; ++k) acc[0] = fmaf(w2t[(int64_t)k * hidden + r], h1[k], acc[0]);
     const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b2[r];
     emb_ws[(int64_t)b * hidden + r] = y / (1.0f + expf(-y));
+    if (sv) sv[in_dim + 2 * hidden + r] = y;
   }
 }
 
@@ -93,17 +100,17 @@ __global__ void __launch_bounds__(TE_THREADS) temb_proj_kernel(const float* __re
 
 using namespace dsg;
 
-extern "C" int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos,
-                              const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t hidden,
-                              const float* wp, const float* bp, int32_t proj_total, float* emb_ws, float* out,
-                              int32_t batch, void* stream) {
+extern "C" int dsg_time_embed_ex(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos,
+                                 const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t hidden,
+                                 const float* wp, const float* bp, int32_t proj_total, float* emb_ws, float* out,
+                                 int32_t batch, float* saved, void* stream) {
   DSG_CHECK_ARG(t && freqs && w1t && b1 && w2t && b2 && wp && bp && emb_ws && out, "dsg_time_embed: null pointer");
   DSG_CHECK_ARG(half > 0 && hidden > 0 && hidden <= 2048 && proj_total > 0 && batch >= 0,
                 "dsg_time_embed: bad sizes");
   if (batch == 0) return DSG_OK;
   const size_t sm1 = (size_t)(2 * half + hidden) * sizeof(float);
   temb_mlp_kernel<<<batch, TE_THREADS, sm1, (cudaStream_t)stream>>>(t, freqs, half, flip_sin_to_cos, w1t, b1, w2t,
-                                                                    b2, hidden, emb_ws);
+                                                                    b2, hidden, emb_ws, saved);
   DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/mlp");
   const size_t sm2 = (size_t)TP_BT * hidden * sizeof(float);
   if (sm2 > 48 * 1024)
@@ -113,4 +120,12 @@ extern "C" int dsg_time_embed(const float* t, const float* freqs, int32_t half, 
       emb_ws, wp, bp, hidden, proj_total, out, batch);
   DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/proj");
   return DSG_OK;
+}
+
+extern "C" int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos,
+                              const float* w1t, const float* b1, const float* w2t, const float* b2, int32_t hidden,
+                              const float* wp, const float* bp, int32_t proj_total, float* emb_ws, float* out,
+                              int32_t batch, void* stream) {
+  return dsg_time_embed_ex(t, freqs, half, flip_sin_to_cos, w1t, b1, w2t, b2, hidden, wp, bp, proj_total, emb_ws, out,
+                           batch, nullptr, stream);
 }

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, DsgError, check
+from ._lib import ConvArgs, DsgError, WgradArgs, check
 
 
 def _st(t: torch.Tensor) -> int:
@@ -129,7 +129,10 @@ def pack_conv_weight(mode: int, w, w_sc=None):
     if w_sc is not None:
         w_sc = w_sc.float().reshape(cout, -1).contiguous()
         csc = w_sc.shape[1]
-    k, rows = lib.dsg_packed_k(mode, cin, csc), lib.dsg_packed_rows(mode, cout)
+    if mode >= 10:
+        k, rows = lib.dsg_packed_k_dgrad(mode - 10, cout), lib.dsg_packed_rows_dgrad(mode - 10, cin)
+    else:
+        k, rows = lib.dsg_packed_k(mode, cin, csc), lib.dsg_packed_rows(mode, cout)
     out = torch.empty((rows, k), dtype=torch.float16, device=w.device)
     check(lib.dsg_pack_conv_weight(mode, w.data_ptr(), cout, cin, _p(w_sc), csc, out.data_ptr(), _st(w)), "pack")
     return out
@@ -142,7 +145,7 @@ def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int =
     _cuda(x, wpacked, bias, temb, residual, sc1, sc2)
     lib = _lib.load()
     n, h, w, cin = x.shape
-    oh, ow = (h // 2, w // 2) if mode == 1 else ((h * 2, w * 2) if mode == 2 else (h, w))
+    oh, ow = (h // 2, w // 2) if mode in (1, 4) else ((h * 2, w * 2) if mode == 2 else (h, w))
     out = torch.empty((n, oh, ow, cout), dtype=torch.float16, device=x.device)
     a = ConvArgs()
     a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, n, h, w, cin, cout
@@ -190,3 +193,172 @@ def attention(qkv, heads: int, head_dim: int, impl: int = 0, dbg=None):
     check(lib.dsg_attention_ex(qkv.data_ptr(), out.data_ptr(), n, tokens, heads, head_dim, impl, _p(dbg), _st(qkv)),
           "attention")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training path
+def grad_scale(dout):
+    """power-of-two scale pair {s, 1/s} (device float[2]) with amax(|dout|) * s in [1, 2)."""
+    _cuda(dout)
+    lib = _lib.load()
+    parts = 148 * 4
+    partial = torch.empty(parts, dtype=torch.float32, device=dout.device)
+    scale = torch.empty(2, dtype=torch.float32, device=dout.device)
+    check(lib.dsg_grad_scale(dout.data_ptr(), dout.numel(), partial.data_ptr(), parts, scale.data_ptr(), _st(dout)),
+          "grad_scale")
+    return scale
+
+
+def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=None, stats2=None, addend=None,
+           dx1=None, dx2=None, acc1=False, acc2=False, want_colsum=False, inv_scale=None):
+    """GroupNorm(+SiLU) backward.  Returns (dx1, dx2, dgamma, dbeta, colsum_per_sample or None)."""
+    _cuda(dy, x1, x2, gamma, beta, addend)
+    lib = _lib.load()
+    n, h, w, c1 = x1.shape
+    c2 = 0 if x2 is None else x2.shape[3]
+    c, hw = c1 + c2, h * w
+    if stats1 is None:
+        stats1 = gn_stats(x1)
+    if x2 is not None and stats2 is None:
+        stats2 = gn_stats(x2)
+    chunks = max(1, min(64, (148 * 4) // n, -(-hw // 64)))
+    partial = torch.empty((n, chunks, c, 2), dtype=torch.float32, device=dy.device)
+    if dx1 is None:
+        dx1 = torch.empty_like(x1)
+    if x2 is not None and dx2 is None:
+        dx2 = torch.empty_like(x2)
+    parts = max(1, min((148 * 4) // n, -(-hw // 32))) if want_colsum else 0
+    colsum = torch.empty((n, parts, c), dtype=torch.float32, device=dy.device) if want_colsum else None
+    check(lib.dsg_gn_bwd(dy.data_ptr(), x1.data_ptr(), c1, stats1.data_ptr(), _p(x2), c2, _p(stats2), gamma.data_ptr(),
+                         beta.data_ptr(), eps, act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1),
+                         _p(dx2), int(acc2), _p(colsum), parts, n, hw, groups, _st(dy)), "gn_bwd")
+    dgamma = torch.empty(c, dtype=torch.float32, device=dy.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=dy.device)
+    check(lib.dsg_gn_bwd_params(partial.data_ptr(), n * chunks, c, _p(inv_scale), dgamma.data_ptr(), dbeta.data_ptr(),
+                                _st(dy)), "gn_bwd_params")
+    per_n = None
+    if want_colsum:
+        per_n = torch.empty((n, c), dtype=torch.float32, device=dy.device)
+        check(lib.dsg_colsum_finalize(colsum.data_ptr(), n, parts, c, per_n.data_ptr(), c, 0, None, None, None,
+                                      _st(dy)), "colsum_finalize")
+    return dx1, dx2, dgamma, dbeta, per_n
+
+
+def colsum(x, inv_scale=None):
+    """sum over all leading dims of an fp16 [..., c] tensor -> fp32 [c]."""
+    _cuda(x)
+    lib = _lib.load()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    parts = max(1, min(148 * 4, -(-rows // 64)))
+    partial = torch.empty((parts, c), dtype=torch.float32, device=x.device)
+    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    check(lib.dsg_colsum_h16(x.data_ptr(), rows, c, partial.data_ptr(), parts, _st(x)), "colsum_h16")
+    check(lib.dsg_colsum_finalize(partial.data_ptr(), 1, parts, c, None, 0, 0, _p(inv_scale), out.data_ptr(), None,
+                                  _st(x)), "colsum_finalize")
+    return out
+
+
+def conv_wgrad(mode: int, x, dy, ci_total: int = 0, ci_off: int = 0, grad=None, accumulate=False, inv_scale=None,
+               impl: int = 0):
+    """weight gradient of a dsg_conv-style conv: x fp16 NHWC (forward input), dy fp16 NHWC (output gradient) ->
+    fp32 OIHW [cout, ci_total, 3, 3] (mode 3: [cout, ci_total])."""
+    _cuda(x, dy)
+    lib = _lib.load()
+    n, h, w, cin = x.shape
+    cout = dy.shape[3]
+    ci_total = ci_total or cin
+    if grad is None:
+        shape = (cout, ci_total) if mode == 3 else (cout, ci_total, 3, 3)
+        grad = torch.zeros(shape, dtype=torch.float32, device=x.device)
+    nbytes = max(16, lib.dsg_wgrad_workspace_bytes(mode, n, h, w, cin, cout))
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+    a = WgradArgs()
+    a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, n, h, w, cin, cout
+    a.x, a.dy, a.grad = x.data_ptr(), dy.data_ptr(), grad.data_ptr()
+    a.ci_total, a.ci_off, a.accumulate = ci_total, ci_off, int(accumulate)
+    a.inv_scale = _p(inv_scale)
+    a.workspace, a.workspace_bytes, a.impl = ws.data_ptr(), nbytes, impl
+    check(lib.dsg_conv_wgrad(C.byref(a), _st(x)), "conv_wgrad")
+    return grad
+
+
+def conv_out_dgrad(dout_nchw, w, scale=None):
+    """data gradient of conv_out: dout fp32 NCHW [n,cout,h,w], w fp32 [cout,cin,3,3] -> fp16 NHWC [n,h,w,cin] (* s)."""
+    _cuda(dout_nchw, w)
+    lib = _lib.load()
+    cout, cin = w.shape[0], w.shape[1]
+    wt = torch.empty((cin, cout, 3, 3), dtype=torch.float32, device=w.device)
+    check(lib.dsg_conv_out_dgrad_weight(w.contiguous().data_ptr(), cout, cin, _p(scale), wt.data_ptr(), _st(w)),
+          "conv_out_dgrad_weight")
+    return conv_in(dout_nchw, wt, torch.zeros(cin, dtype=torch.float32, device=w.device))
+
+
+def small_wgrad(wide, narrow, conv_out_form: bool, inv_scale=None):
+    """conv_in / conv_out weight gradient.  wide fp16 NHWC [n,h,w,wc], narrow fp32 NCHW [n,nc,h,w]."""
+    _cuda(wide, narrow)
+    lib = _lib.load()
+    n, h, w, wc = wide.shape
+    nc = narrow.shape[1]
+    parts = min(n * h, 148 * 4)
+    partial = torch.empty((parts, nc * 9 * wc + nc), dtype=torch.float32, device=wide.device)
+    dw = torch.empty((nc, wc, 3, 3) if conv_out_form else (wc, nc, 3, 3), dtype=torch.float32, device=wide.device)
+    nsum = torch.empty(nc, dtype=torch.float32, device=wide.device)
+    check(lib.dsg_small_wgrad(wide.data_ptr(), narrow.data_ptr(), n, h, w, wc, nc, int(conv_out_form),
+                              partial.data_ptr(), parts, _p(inv_scale), dw.data_ptr(), nsum.data_ptr(), _st(wide)),
+          "small_wgrad")
+    return dw, nsum
+
+
+def attention_bwd(qkv, out, dout, heads: int, head_dim: int):
+    _cuda(qkv, out, dout)
+    lib = _lib.load()
+    n, tokens, _ = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(2 * n * heads * tokens, dtype=torch.float32, device=qkv.device)
+    check(lib.dsg_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), n,
+                                tokens, heads, head_dim, _st(qkv)), "attention_bwd")
+    return dqkv
+
+
+def lin_dgrad_small(dy, w, pre=None, dy_off: int = 0, rows: int = 0):
+    _cuda(dy, w, pre)
+    lib = _lib.load()
+    rows = rows or w.shape[0]
+    cols = w.shape[1]
+    batch = dy.shape[0]
+    dx = torch.empty((batch, cols), dtype=torch.float32, device=dy.device)
+    check(lib.dsg_lin_dgrad_small(dy.data_ptr(), dy.shape[1], dy_off, w.data_ptr(), rows, cols, _p(pre), dx.data_ptr(),
+                                  batch, _st(dy)), "lin_dgrad_small")
+    return dx
+
+
+def lin_wgrad_small(dy, x, rows: int = 0, dy_off: int = 0, inv_scale=None):
+    _cuda(dy, x)
+    lib = _lib.load()
+    rows = rows or dy.shape[1]
+    cols, batch = x.shape[1], dy.shape[0]
+    dw = torch.empty((rows, cols), dtype=torch.float32, device=dy.device)
+    db = torch.empty(rows, dtype=torch.float32, device=dy.device)
+    check(lib.dsg_lin_wgrad_small(dy.data_ptr(), dy.shape[1], dy_off, x.data_ptr(), x.shape[1], rows, cols, batch,
+                                  _p(inv_scale), dw.data_ptr(), db.data_ptr(), _st(dy)), "lin_wgrad_small")
+    return dw, db
+
+
+def grad_norm(g, inv_loss_scale: float = 1.0, max_norm: float = 0.0):
+    """device float[3] = {norm, unscale-and-clip coefficient, nonfinite flag} of a flat fp32 gradient buffer."""
+    _cuda(g)
+    lib = _lib.load()
+    parts = 148 * 8
+    partial = torch.empty(parts, dtype=torch.float64, device=g.device)
+    out = torch.empty(3, dtype=torch.float32, device=g.device)
+    check(lib.dsg_grad_norm(g.data_ptr(), g.numel(), partial.data_ptr(), parts, inv_loss_scale, max_norm,
+                            out.data_ptr(), _st(g)), "grad_norm")
+    return out
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step: int, ctl=None):
+    _cuda(p, g, m, v, ctl)
+    lib = _lib.load()
+    check(lib.dsg_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                             weight_decay, step, _p(ctl), _st(p)), "adamw_step")

@@ -88,7 +88,9 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores (TMA -> smem -> UMMA -> TMEM -> epilogue).
  * mode: 0 = 3x3 stride 1 pad 1, 1 = 3x3 stride 2 pad 1, 2 = nearest-2x upsample followed by 3x3 pad 1
- *       (evaluated as four 2x2 sub-pixel convolutions on pre-summed weights), 3 = 1x1.
+ *       (evaluated as four 2x2 sub-pixel convolutions on pre-summed weights), 3 = 1x1,
+ *       4 = the adjoint of mode 2 (4x4 stride-2 gather over the four parity views of x; output h/2 x w/2) — used
+ *       for the data gradient of the upsample conv with weights packed in mode 12.
  * x: h16 [n][h][w][cin].  sc1/sc2: optional extra 1x1 ("conv_shortcut") inputs at the OUTPUT resolution whose
  * channels are appended to the GEMM K dimension (sc2 may be NULL; csc2 = 0).  residual: optional h16 tensor shaped
  * like the output, added in the epilogue.  bias: float[cout].  temb: optional float[n][temb_stride], element
@@ -109,10 +111,12 @@ typedef struct dsg_conv_args {
   const void* residual;
   void* out;
   int32_t block_n; /* 0 = auto, else 64/128/256 */
-  int32_t impl;    /* 0 = tcgen05 path (halo-reuse kernel where it applies, else the tap-streaming kernel),
+  int32_t impl;    /* 0 = tcgen05 path (CTA-pair halo-reuse kernel where it applies, else the single-CTA halo-reuse
+                      kernel, else the tap-streaming kernel),
                       1 = plain CUDA-core cross-check kernel (slow; debugging/tests only),
-                      2 = force the tap-streaming tcgen05 kernel, 3 = force the halo-reuse tcgen05 kernel
-                      (DSG_ERR_UNSUPPORTED when the mode/shape is outside it: modes 0 and 2, W >= 8, H >= tile) */
+                      2 = force the tap-streaming tcgen05 kernel, 3 = force the single-CTA halo-reuse tcgen05 kernel,
+                      4 = force the CTA-pair (cta_group::2) halo-reuse kernel
+                      (3/4: DSG_ERR_UNSUPPORTED when the mode/shape is outside it: modes 0 and 2, W >= 8, H >= tile) */
   /* conv_out form (replaces UNet2DModel.conv_out, 64 -> 3 channels): when out_nchw_f32 is non-NULL the weights are
    * packed for cout = 16 (rows >= cout_real are zero), mode must be 0, `out` is ignored and the first cout_real
    * output channels are written as NCHW fp32 [n][cout_real][h][w].  Halo-reuse kernel only (W >= 8, H >= 18). */
@@ -128,6 +132,12 @@ int dsg_conv(const dsg_conv_args* args, void* stream);
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */
 int64_t dsg_packed_k(int32_t mode, int32_t cin, int32_t csc);
 int64_t dsg_packed_rows(int32_t mode, int32_t cout);
+/* Data-gradient ("dgrad") packings: dsg_pack_conv_weight modes 10..13 take the SAME fp32 OIHW weight as modes 0..3
+ * (cout / cin are the forward conv's) and produce the weights of the conv that maps the OUTPUT gradient to the INPUT
+ * gradient: 10 -> run dsg_conv mode 0 (cin' = cout, cout' = cin), 11 -> mode 2 over the low-resolution gradient,
+ * 12 -> mode 4 over the high-resolution gradient, 13 -> mode 3.  K / rows of those packings: */
+int64_t dsg_packed_k_dgrad(int32_t fwd_mode, int32_t cout);
+int64_t dsg_packed_rows_dgrad(int32_t fwd_mode, int32_t cin);
 /* Pack fp32 OIHW conv weights (+ optional 1x1 shortcut weights [cout][csc]) into the h16 GEMM layout.
  * All pointers are device pointers. */
 int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_t cin, const float* w_sc,
@@ -143,6 +153,106 @@ int dsg_attention(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t
  * un-normalised output tile (column 8 = softmax denominator) of the first (sample, head). */
 int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
                      int32_t impl, float* dbg, void* stream);
+
+
+/* ================================================================ training path (backward + optimizer) ==========
+ * Replaces what torch autograd / cuDNN / torch.optim run behind `accelerator.backward(loss)`,
+ * `accelerator.clip_grad_norm_` and `optimizer.step()` (DriveSceneGen/pipeline/training_pipeline.py:86-89) for the
+ * UNet2DModel of DriveSceneGen/scripts/train.py:39-57.  Activation gradients are h16 like the activations and are
+ * carried times a power-of-two factor s (dsg_grad_scale); every parameter-gradient entry point takes `inv_scale`, a
+ * DEVICE pointer to 1/s (NULL = 1), and writes fp32 gradients in the parameter's own (torch) layout. */
+
+/* scale[0] = s, scale[1] = 1/s with amax(|dout|) * s in [1, 2) (s = 1 when amax is 0 or not finite).
+ * partial: float[parts] scratch. */
+int dsg_grad_scale(const float* dout, int64_t numel, float* partial, int32_t parts, float* scale, void* stream);
+
+/* same as dsg_time_embed; saved (may be NULL): float[batch][2*half + 3*hidden] = per sample
+ * [ sinusoid | pre-activation of linear_1 | SiLU of it | pre-activation of linear_2 ] for the backward. */
+int dsg_time_embed_ex(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos, const float* w1t,
+                      const float* b1, const float* w2t, const float* b2, int32_t hidden, const float* wp,
+                      const float* bp, int32_t proj_total, float* emb_ws, float* out, int32_t batch, float* saved,
+                      void* stream);
+/* small-batch fp32 linear backward (time-embedding path).  w is [rows][cols] = torch [out][in].
+ *   dgrad: dx[n][k] = (sum_r dy[n][dy_off + r] * w[r][k]) * (pre ? SiLU'(pre[n][k]) : 1)
+ *   wgrad: dw[r][k] = inv_scale * sum_n dy[n][dy_off + r] * x[n][k];  db[r] = inv_scale * sum_n dy[n][dy_off + r] */
+int dsg_lin_dgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const float* w, int32_t rows, int32_t cols,
+                        const float* pre, float* dx, int32_t batch, void* stream);
+int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const float* x, int32_t ldx, int32_t rows,
+                        int32_t cols, int32_t batch, const float* inv_scale, float* dw, float* db /* may be NULL */,
+                        void* stream);
+
+/* GroupNorm(+SiLU) backward over cat(x1, x2) (see dsg_gn_apply for the forward and the statistics format).
+ *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: float[n][chunks][c1+c2][2] scratch that
+ *   afterwards holds the per-(sample, chunk) sums behind d beta / d gamma (dsg_gn_bwd_params), 1 <= chunks <= 64.
+ *   addend (may be NULL): h16 [n][hw][c1+c2] added to the input gradient (the ResnetBlock shortcut's gradient).
+ *   dx1 / dx2: h16 gradients of x1 / x2; accN != 0 adds to the existing content (tensor with two consumers).
+ *   colsum (may be NULL, then colsum_parts = 0): float[n][colsum_parts][c1+c2] receives per-CTA column sums of the
+ *   GroupNorm term of dx (before addend / accumulate) — the time-embedding / conv bias gradient of a ResnetBlock;
+ *   colsum_parts is also the number of CTAs per sample of the apply pass. */
+int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
+               const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
+               int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
+               int32_t colsum_parts, int32_t n, int64_t hw, int32_t groups, void* stream);
+/* d gamma[c] / d beta[c] = inv_scale * sum over rows (= n * chunks) of partial[row][c][1 / 0] */
+int dsg_gn_bwd_params(const float* partial, int32_t rows, int32_t c, const float* inv_scale, float* dgamma,
+                      float* dbeta, void* stream);
+/* column sums of an h16 [rows][c] tensor: partial float[parts][c] */
+int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32_t parts, void* stream);
+/* partial float[n][parts][c] -> per_n[i][per_n_off + c] (raw per-sample sums, may be NULL) and
+ * total[c] = total2[c] = inv_scale * sum over samples and parts (either may be NULL) */
+int dsg_colsum_finalize(const float* partial, int32_t n, int32_t parts, int32_t c, float* per_n, int32_t per_n_stride,
+                        int32_t per_n_off, const float* inv_scale, float* total, float* total2, void* stream);
+
+/* Weight gradient of a dsg_conv-style convolution on tcgen05 tensor cores (pixel axis = GEMM K, split over CTAs,
+ * deterministic two-stage reduction).  mode = the FORWARD conv's mode (0, 1, 2, 3); n, h, w, cin describe the forward
+ * input x (h16 [n][h][w][cin]); dy is the h16 output gradient ([n][h][w][cout], [n][h/2][w/2][cout] for mode 1,
+ * [n][2h][2w][cout] for mode 2).  grad: fp32 OIHW [cout][ci_total][3][3] ([cout][ci_total] for mode 3); this call
+ * fills input-channel columns [ci_off, ci_off + cin) — a conv_shortcut over cat(x1, x2) takes one call per source.
+ * workspace: >= dsg_wgrad_workspace_bytes(...) bytes, 16-byte aligned.  impl: 0 = auto (tcgen05 when W >= 8 and
+ * H >= pixel tile + 2, else the CUDA-core kernel), 1 = CUDA-core cross-check kernel, 2 = tcgen05 or error. */
+typedef struct dsg_wgrad_args {
+  int32_t mode;
+  int32_t n, h, w, cin, cout;
+  const void* x;
+  const void* dy;
+  float* grad;
+  int32_t ci_total, ci_off;
+  int32_t accumulate; /* 0 = overwrite, 1 = add to grad */
+  const float* inv_scale;
+  void* workspace;
+  int64_t workspace_bytes;
+  int32_t impl;
+} dsg_wgrad_args;
+int dsg_conv_wgrad(const dsg_wgrad_args* args, void* stream);
+int64_t dsg_wgrad_workspace_bytes(int32_t mode, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout);
+
+/* conv_out data gradient = dsg_conv_in over the fp32 NCHW output gradient with wt = s * flipped, transposed
+ * conv_out weight: w fp32 [cout][cin][3][3] -> wt fp32 [cin][cout][3][3]; scale = device pointer to s (NULL = 1). */
+int dsg_conv_out_dgrad_weight(const float* w, int32_t cout, int32_t cin, const float* scale, float* wt, void* stream);
+/* Weight gradient of conv_in / conv_out: wide = the h16 [n][h][w][wc] side, narrow = the fp32 NCHW [n][nc][h][w] side.
+ *   conv_out_form = 0 (conv_in):  dw fp32 [wc][nc][3][3] = inv_scale * sum wide[q][wc] * narrow[c][q + tap]
+ *   conv_out_form = 1 (conv_out): dw fp32 [nc][wc][3][3] = inv_scale * sum wide[q + tap][wc] * narrow[c][q]
+ * narrow_sum (may be NULL): float[nc] plain sums of the narrow tensor (conv_out's bias gradient).
+ * partial: float[parts][nc*9*wc + nc] scratch; parts = number of CTAs (grid-stride over image rows). */
+int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, int32_t h, int32_t w, int32_t wc,
+                    int32_t nc, int32_t conv_out_form, float* partial, int32_t parts, const float* inv_scale, float* dw,
+                    float* narrow_sum, void* stream);
+
+/* Backward of dsg_attention (head_dim 8 only): dqkv h16 [n][tokens][3*c] from qkv, the forward output `out` and its
+ * gradient `dout` (both h16 [n][tokens][c]).  ws: float[2 * n * heads * tokens] scratch. */
+int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t n,
+                      int32_t tokens, int32_t heads, int32_t head_dim, void* stream);
+
+/* Global gradient norm over one flat fp32 buffer: out3 = { ||g|| * inv_loss_scale, coefficient that unscales and clips
+ * (inv_loss_scale * min(1, max_norm / (norm + 1e-6)); max_norm <= 0 disables clipping), 1 if the norm is inf/nan }.
+ * partial: double[parts] scratch.  Deterministic (fixed-order sums). */
+int dsg_grad_norm(const float* g, int64_t numel, double* partial, int32_t parts, float inv_loss_scale, float max_norm,
+                  float* out3, void* stream);
+/* torch.optim.AdamW step (decoupled weight decay, bias correction, no amsgrad) over flat buffers; step >= 1.
+ * ctl (may be NULL): device float[3] from dsg_grad_norm — gradients are multiplied by ctl[1] and the whole update is
+ * skipped when ctl[2] != 0 (GradScaler semantics). */
+int dsg_adamw_step(float* p, const float* g, float* m, float* v, int64_t numel, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int32_t step, const float* ctl, void* stream);
 
 #ifdef __cplusplus
 }
