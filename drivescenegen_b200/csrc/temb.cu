@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
                                                               const float* __restrict__ w2t, const float* __restrict__ b2,
                                                               int hidden, float* __restrict__ emb_ws,
                                                               float* __restrict__ saved) {
-  // saved (training only, may be NULL): per sample [ sinusoid (2*half) | pre1 | SiLU(pre1) | pre2 ] (hidden each)
+  // saved (training only, may be NULL): four dense arrays [batch][2*half] sinusoid, then [batch][hidden] each of
+  // pre1, SiLU(pre1), pre2
   extern __shared__ float sm[];
   float* e = sm;               // [2*half]
   float* h1 = sm + 2 * half;   // [hidden]
@@ -30,9 +31,11 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     e[flip ? i : half + i] = c;
   }
   __syncthreads();
-  float* sv = saved ? saved + (int64_t)b * (in_dim + 3 * hidden) : nullptr;
-  if (sv)
-    for (int i = threadIdx.x; i < in_dim; i += blockDim.x) sv[i] = e[i];
+  const int64_t nb = gridDim.x;
+  float* sv_e = saved ? saved + (int64_t)b * in_dim : nullptr;
+  float* sv_h = saved ? saved + nb * in_dim + (int64_t)b * hidden : nullptr;  // + k * nb * hidden for array k
+  if (saved)
+    for (int i = threadIdx.x; i < in_dim; i += blockDim.x) sv_e[i] = e[i];
   for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     int k = 0;
@@ -43,7 +46,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     for (; k < in_dim; ++k) acc[0] = fmaf(w1t[(int64_t)k * hidden + r], e[k], acc[0]);
     const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b1[r];
     h1[r] = y / (1.0f + expf(-y));
-    if (sv) { sv[in_dim + r] = y; sv[in_dim + hidden + r] = h1[r]; }
+    if (saved) { sv_h[r] = y; sv_h[nb * hidden + r] = h1[r]; }
   }
   __syncthreads();
   for (int r = threadIdx.x; r < hidden; r += blockDim.x) {
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
     for (; k < hidden; ++k) acc[0] = fmaf(w2t[(int64_t)k * hidden + r], h1[k], acc[0]);
     const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b2[r];
     emb_ws[(int64_t)b * hidden + r] = y / (1.0f + expf(-y));
-    if (sv) sv[in_dim + 2 * hidden + r] = y;
+    if (saved) sv_h[2 * nb * hidden + r] = y;
   }
 }
 

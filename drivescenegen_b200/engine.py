@@ -70,6 +70,8 @@ class UNetEngine:
         self.packed = False
         self.conv_impl = 0       # 0 = tcgen05 igemm, 1 = plain CUDA cross-check kernel (tests only)
         self.block_n_override = 0
+        self.train_packs = False  # also pack the data-gradient forms of every conv weight (training path)
+        self.train_programs: Dict[Tuple[int, int, int, int], object] = {}
         self._build_topology()
 
     # ------------------------------------------------------------------ topology (mirrors upstream __init__)
@@ -145,29 +147,59 @@ class UNetEngine:
             csc = int(w_sc.shape[1])
         k = self.lib.dsg_packed_k(mode, cin, csc)
         rows = self.lib.dsg_packed_rows(mode, cout)
-        out = torch.empty(rows * k, dtype=torch.float16, device=self.device)
+        out = self._weight_buf(name, rows * k, torch.float16)
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self.lib.dsg_pack_conv_weight(mode, w.data_ptr(), cout, cin, _p(w_sc), csc, out.data_ptr(), st),
               f"pack {name}")
         self.weights[name] = out
 
+    def _pack_dgrad(self, name: str, fwd_mode: int, w: torch.Tensor):
+        """data-gradient packing of a conv weight (pack modes 10-13, include/dsg_b200.h)."""
+        w = w.detach().to(self.device, torch.float32).contiguous()
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        k = self.lib.dsg_packed_k_dgrad(fwd_mode, cout)
+        rows = self.lib.dsg_packed_rows_dgrad(fwd_mode, cin)
+        out = self._weight_buf(name, rows * k, torch.float16)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.dsg_pack_conv_weight(10 + fwd_mode, w.data_ptr(), cout, cin, None, 0, out.data_ptr(), st),
+              f"pack dgrad {name}")
+        self.weights[name] = out
+
+    def _weight_buf(self, name: str, numel: int, dtype) -> torch.Tensor:
+        """Packed-weight buffers keep their address across re-packs (a training step re-packs every step, and the
+        execution programs hold raw pointers); a new or resized buffer invalidates the programs."""
+        t = self.weights.get(name)
+        if t is None or t.numel() != numel or t.dtype != dtype:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self.weights[name] = t
+            self._new_weight_buffers = True
+        return t
+
     def _f32(self, name: str, t: torch.Tensor):
-        self.weights[name] = t.detach().to(self.device, torch.float32).contiguous().clone()
+        t = t.detach()
+        buf = self._weight_buf(name, t.numel(), torch.float32)
+        if buf.shape != t.shape:
+            buf = buf.view(t.shape)
+            self.weights[name] = buf
+        buf.copy_(t)
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         """(Re)pack all weights from a state dict with upstream key names."""
+        self._new_weight_buffers = False
         with torch.cuda.device(self.device):
             self._f32("conv_in.w", sd["conv_in.weight"])
             self._f32("conv_in.b", sd["conv_in.bias"])
             self._f32("conv_out.w", sd["conv_out.weight"])
             self._f32("conv_out.b", sd["conv_out.bias"])
             # tensor-core form of conv_out: output channels zero-padded to the smallest UMMA N (16)
-            wo = sd["conv_out.weight"].detach().float()
+            wo = sd["conv_out.weight"].detach().to(self.device, torch.float32)
             if wo.shape[0] <= 16 and wo.shape[1] % 64 == 0:
-                w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float32)
-                w16[: wo.shape[0]] = wo.cpu()
-                b16 = torch.zeros(16, dtype=torch.float32)
-                b16[: wo.shape[0]] = sd["conv_out.bias"].detach().float().cpu()
+                w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float32, device=self.device)
+                w16[: wo.shape[0]] = wo
+                b16 = torch.zeros(16, dtype=torch.float32, device=self.device)
+                b16[: wo.shape[0]] = sd["conv_out.bias"].detach().to(self.device, torch.float32)
                 self._pack_conv("conv_out.w16", 0, w16)
                 self._f32("conv_out.b16", b16)
             self._f32("norm_out.g", sd["conv_norm_out.weight"])
@@ -199,7 +231,11 @@ class UNetEngine:
                 # global loads in the epilogue, which those short-K tiles cannot hide.
                 r["id_sc"] = (not has_sc) and r["cout"] <= 128
                 if r["id_sc"]:
-                    w_sc = torch.eye(r["cout"], dtype=torch.float32)
+                    if not hasattr(self, "_eye"):
+                        self._eye = {}
+                    if r["cout"] not in self._eye:
+                        self._eye[r["cout"]] = torch.eye(r["cout"], dtype=torch.float32, device=self.device)
+                    w_sc = self._eye[r["cout"]]
                 else:
                     w_sc = sd[sc_key] if has_sc else None
                 self._pack_conv(f"{pre}.conv2", 0, sd[f"{pre}.conv2.weight"], w_sc)
@@ -208,6 +244,11 @@ class UNetEngine:
                     b2 = b2 + sd[f"{pre}.conv_shortcut.bias"].detach().to(self.device, torch.float32)
                 self._f32(f"{pre}.conv2.b", b2)
                 r["has_sc"] = has_sc
+                if self.train_packs:
+                    self._pack_dgrad(f"{pre}.conv1.dg", 0, sd[f"{pre}.conv1.weight"])
+                    self._pack_dgrad(f"{pre}.conv2.dg", 0, sd[f"{pre}.conv2.weight"])
+                    if has_sc:
+                        self._pack_dgrad(f"{pre}.sc.dg", 3, sd[sc_key])
             attns = [a for blk in self.down for a in blk["attn"]] + ([self.mid["attn"]] if self.mid["attn"] else []) \
                 + [a for blk in self.up for a in blk["attn"]]
             for a in attns:
@@ -220,18 +261,30 @@ class UNetEngine:
                 self._f32(f"{pre}.qkv.b", bqkv)
                 self._pack_conv(f"{pre}.out", 3, sd[f"{pre}.to_out.0.weight"])
                 self._f32(f"{pre}.out.b", sd[f"{pre}.to_out.0.bias"])
+                if self.train_packs:
+                    self._pack_dgrad(f"{pre}.qkv.dg", 3, wqkv)
+                    self._pack_dgrad(f"{pre}.out.dg", 3, sd[f"{pre}.to_out.0.weight"])
             for i, blk in enumerate(self.down):
                 if blk["down"]:
                     pre = f"down_blocks.{i}.downsamplers.0.conv"
                     self._pack_conv(pre, 1, sd[pre + ".weight"])
                     self._f32(pre + ".b", sd[pre + ".bias"])
+                    if self.train_packs:
+                        self._pack_dgrad(pre + ".dg", 1, sd[pre + ".weight"])
             for i, blk in enumerate(self.up):
                 if blk["up"]:
                     pre = f"up_blocks.{i}.upsamplers.0.conv"
                     self._pack_conv(pre, 2, sd[pre + ".weight"])
                     self._f32(pre + ".b", sd[pre + ".bias"])
+                    if self.train_packs:
+                        self._pack_dgrad(pre + ".dg", 2, sd[pre + ".weight"])
+        if self.train_packs:
+            for k in ("linear_1", "linear_2"):
+                self._f32(f"te.{k}.w_oi", sd[f"time_embedding.{k}.weight"])   # [out][in] for the backward
         self.packed = True
-        self.programs.clear()  # programs hold raw weight pointers
+        if self._new_weight_buffers:   # programs hold raw weight pointers
+            self.programs.clear()
+            self.train_programs.clear()
 
     # ------------------------------------------------------------------ program construction
     def program(self, batch: int, h: int, w: int) -> "_Program":
@@ -245,6 +298,22 @@ class UNetEngine:
                 raise DsgError(f"input {h}x{w} must be divisible by {div}")
             prog = _Program(self, batch, h, w)
             self.programs[key] = prog
+        return prog
+
+    def train_program(self, batch: int, h: int, w: int, grad_slices: Dict[str, torch.Tensor], slot: int = 0):
+        """forward-with-saved-activations + backward program (engine_train.TrainProgram) writing parameter
+        gradients into grad_slices (name -> fp32 view); one program per (shape, gradient-buffer slot)."""
+        from .engine_train import TrainProgram
+        key = (batch, h, w, slot)
+        prog = self.train_programs.get(key)
+        if prog is None:
+            if not self.packed or not self.train_packs:
+                raise DsgError("UNetEngine: training weights have not been packed")
+            div = 2 ** (self.n_levels - 1)
+            if h % div or w % div:
+                raise DsgError(f"input {h}x{w} must be divisible by {div}")
+            prog = TrainProgram(self, batch, h, w, grad_slices)
+            self.train_programs[key] = prog
         return prog
 
     def forward(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -312,6 +381,9 @@ class _Program:
     def _tmp(self, name: str, hw: Tuple[int, int], ch: int) -> torch.Tensor:
         return self._tmp_raw(name, self.b * hw[0] * hw[1] * ch, torch.float16)
 
+    def _te_saved(self, half: int, hidden: int) -> Optional[torch.Tensor]:
+        return None   # inference keeps no time-embedding activations (the training program does)
+
     # --- op emitters ---------------------------------------------------------------------------------
     def _emit(self, name: str, meta: dict, fn: Callable[[int], None]):
         self.ops.append(fn)
@@ -341,6 +413,7 @@ class _Program:
               out.data_ptr(), b, npx, eng.groups)
         nbytes = b * npx * (c1 + c2) * 2
         self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
+        return st1, st2
 
     def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
               sc2=None, csc2=0, count_sc=True, stats=None):
@@ -372,7 +445,7 @@ class _Program:
     def _resnet(self, r, x1, x2, hw, out):
         c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
         act = self._tmp("act", hw, c1 + c2)
-        self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
+        st1, st2 = self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
         hbuf = self._tmp("h", hw, co)
         h_stats = self._stats(co)   # the "h" buffer is shared between blocks, its statistics are not
         self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"],
@@ -384,12 +457,14 @@ class _Program:
                        count_sc=r["has_sc"])
         else:
             self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, residual=x1)
+        return {"kind": "resnet", "r": r, "x1": x1, "x2": x2, "hw": hw, "out": out, "a1": act, "h": hbuf,
+                "h_stats": h_stats, "a2": act2, "st1": st1, "st2": st2}
 
     def _attn(self, a, x, hw, out):
         eng, lib, b = self.eng, self.lib, self.b
         ch, pre, hd = a["ch"], a["prefix"], a["head_dim"]
         act = self._tmp("act", hw, ch)
-        self._gn(x, ch, None, 0, hw, f"{pre}.gn.g", f"{pre}.gn.b", 0, act)
+        st1, _ = self._gn(x, ch, None, 0, hw, f"{pre}.gn.g", f"{pre}.gn.b", 0, act)
         qkv = self._tmp("qkv", hw, 3 * ch)
         self._conv(3, act, hw, ch, 3 * ch, f"{pre}.qkv", f"{pre}.qkv.b", qkv)
         o = self._tmp("attn_o", hw, ch)
@@ -398,6 +473,10 @@ class _Program:
         self._emit("attention", {"flops": 4 * b * ntok * ntok * ch, "exps": b * (ch // hd) * ntok * ntok},
                    lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
         self._conv(3, o, hw, ch, ch, f"{pre}.out", f"{pre}.out.b", out, residual=x)
+        return {"kind": "attn", "a": a, "x": x, "hw": hw, "out": out, "act": act, "qkv": qkv, "o": o, "st1": st1}
+
+    def _record(self, rec: dict):
+        """hook: the training program keeps what each block produced (engine_train.py); inference drops it."""
 
     # --- whole forward -------------------------------------------------------------------------------
     def _build(self):
@@ -413,7 +492,10 @@ class _Program:
                    W["te.proj.w"].data_ptr(), W["te.proj.b"].data_ptr(), eng.proj_total, emb_ws.data_ptr(),
                    self.temb.data_ptr(), b)
         self._emit("zero_stats", {}, lambda st: self.stats_all.zero_())
-        self._emit("time_embed", {}, lambda st: check(lib.dsg_time_embed(self.t_ptr, *te_args, st), "time_embed"))
+        te_saved = self._te_saved(half, eng.temb_hidden)
+        self.emb_ws = emb_ws
+        self._emit("time_embed", {}, lambda st: check(lib.dsg_time_embed_ex(self.t_ptr, *te_args, _p(te_saved), st),
+                                                      "time_embed"))
         c0 = eng.cfg["block_out_channels"][0]
         x = self._new("conv_in", hw, c0)
         ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(), b, self.cin, hw[0], hw[1], c0)
@@ -423,16 +505,17 @@ class _Program:
         gs_args = (x.data_ptr(), c0, self.stats_of[x.data_ptr()].data_ptr(), b, hw[0] * hw[1])
         self._emit("gn_stats", {"bytes": b * hw[0] * hw[1] * c0 * 2},
                    lambda st: check(lib.dsg_gn_stats(*gs_args, st), "gn_stats"))
+        self._record({"kind": "in", "out": x, "hw": hw, "c0": c0})
         skips = [(x, c0, hw)]
         for i, blk in enumerate(eng.down):
             for j, r in enumerate(blk["resnets"]):
                 has_attn = bool(blk["attn"])
                 out = self._new(f"d{i}r{j}" + ("pre" if has_attn else ""), hw, r["cout"])
-                self._resnet(r, x, None, hw, out)
+                self._record(self._resnet(r, x, None, hw, out))
                 x = out
                 if has_attn:
                     out = self._new(f"d{i}a{j}", hw, r["cout"])
-                    self._attn(blk["attn"][j], x, hw, out)
+                    self._record(self._attn(blk["attn"][j], x, hw, out))
                     x = out
                 skips.append((x, r["cout"], hw))
             if blk["down"]:
@@ -440,18 +523,19 @@ class _Program:
                 out = self._new(f"d{i}ds", nhw, blk["ch"])
                 pre = f"down_blocks.{i}.downsamplers.0.conv"
                 self._conv(1, x, hw, blk["ch"], blk["ch"], pre, pre + ".b", out)
+                self._record({"kind": "down", "prefix": pre, "x": x, "hw": hw, "out": out, "ch": blk["ch"]})
                 x, hw = out, nhw
                 skips.append((x, blk["ch"], hw))
         mid = eng.mid
         out = self._new("m0", hw, mid["resnets"][0]["cout"])
-        self._resnet(mid["resnets"][0], x, None, hw, out)
+        self._record(self._resnet(mid["resnets"][0], x, None, hw, out))
         x = out
         if mid["attn"] is not None:
             out = self._new("ma", hw, mid["attn"]["ch"])
-            self._attn(mid["attn"], x, hw, out)
+            self._record(self._attn(mid["attn"], x, hw, out))
             x = out
         out = self._new("m1", hw, mid["resnets"][1]["cout"])
-        self._resnet(mid["resnets"][1], x, None, hw, out)
+        self._record(self._resnet(mid["resnets"][1], x, None, hw, out))
         x = out
         for i, blk in enumerate(eng.up):
             for j, r in enumerate(blk["resnets"]):
@@ -459,21 +543,23 @@ class _Program:
                 assert sk_c == r["cskip"] and sk_hw == hw, (sk_c, r["cskip"], sk_hw, hw)
                 has_attn = bool(blk["attn"])
                 out = self._new(f"u{i}r{j}" + ("pre" if has_attn else ""), hw, r["cout"])
-                self._resnet(r, x, sk, hw, out)
+                self._record(self._resnet(r, x, sk, hw, out))
                 x = out
                 if has_attn:
                     out = self._new(f"u{i}a{j}", hw, r["cout"])
-                    self._attn(blk["attn"][j], x, hw, out)
+                    self._record(self._attn(blk["attn"][j], x, hw, out))
                     x = out
             if blk["up"]:
                 nhw = (hw[0] * 2, hw[1] * 2)
                 out = self._new(f"u{i}us", nhw, blk["ch"])
                 pre = f"up_blocks.{i}.upsamplers.0.conv"
                 self._conv(2, x, hw, blk["ch"], blk["ch"], pre, pre + ".b", out)
+                self._record({"kind": "up", "prefix": pre, "x": x, "hw": hw, "out": out, "ch": blk["ch"]})
                 x, hw = out, nhw
         assert not skips
         act = self._tmp("act", hw, c0)
-        self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
+        st_out, _ = self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
+        self._record({"kind": "out", "x": x, "hw": hw, "act": act, "st1": st_out, "c0": c0})
         tw = 16 if hw[1] >= 16 else (8 if hw[1] >= 8 else 0)
         meta = {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2), "flops": 2 * b * hw[0] * hw[1] * self.cout * 9 * c0}
         if "conv_out.w16" in W and tw and hw[0] >= 2 * (128 // tw) + 2 and eng.conv_impl != 1:

@@ -1,0 +1,419 @@
+"""TrainProgram — the U-Net forward with saved activations plus its hand-written backward, as two flat kernel programs.
+
+Training path of SURVEY.md §8 a17: what torch autograd + cuDNN execute behind ``model(noisy, t)`` /
+``accelerator.backward(loss)`` in ``DriveSceneGen/pipeline/training_pipeline.py:84-86``.  Host-side orchestration only —
+every arithmetic step is a libdsg_b200 call (include/dsg_b200.h, "training path"):
+
+  forward   the same op sequence as inference (``engine._Program``) but every intermediate a backward op needs
+            (GroupNorm+SiLU outputs, conv1 outputs, attention q/k/v and output, time-embedding pre-activations) lives in
+            its own buffer instead of a shared temporary.
+  backward  per block, in reverse order: bias gradients (column sums), weight gradients (tcgen05 ``dsg_conv_wgrad``),
+            data gradients (``dsg_conv`` on the dgrad-packed weights), GroupNorm+SiLU backward (``dsg_gn_bwd``, which
+            also adds the shortcut gradient and accumulates into tensors with two consumers), attention backward,
+            and finally the time-embedding MLP.  Parameter gradients are written in fp32, torch layout, straight into
+            the slices of ONE flat gradient buffer (the single NCCL all-reduce / fused AdamW operate on it).
+
+Activation gradients are fp16 times a power-of-two factor chosen per step from the incoming gradient (``dsg_grad_scale``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from ._lib import ConvArgs, WgradArgs, check
+from .engine import UNetEngine, _Program, _p
+
+
+class TrainProgram(_Program):
+    def __init__(self, eng: UNetEngine, batch: int, h: int, w: int, grad_slices: Dict[str, torch.Tensor]):
+        """grad_slices: parameter name (upstream state-dict key) -> fp32 view that receives its gradient."""
+        self.grads = grad_slices
+        self.records: List[dict] = []
+        self.bwd_ops: List[Callable[[int], None]] = []
+        self.bwd_info: List[Tuple[str, dict]] = []
+        self._uid = 0
+        self.dout_ptr = C.c_void_p(0)
+        super().__init__(eng, batch, h, w)
+        self._build_backward()
+
+    # ------------------------------------------------------------------ forward: every temporary is persistent
+    def _build(self):
+        self._uid = 0
+        self.records = []
+        super()._build()
+
+    def _tmp(self, name: str, hw: Tuple[int, int], ch: int) -> torch.Tensor:
+        self._uid += 1
+        numel = self.b * hw[0] * hw[1] * ch
+        return self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/{name}{self._uid}", numel, torch.float16)
+
+    def _te_saved(self, half: int, hidden: int) -> Optional[torch.Tensor]:
+        self.te_saved = self.eng.arena.get(f"train/{self.b}/te_saved", self.b * (2 * half + 3 * hidden), torch.float32)
+        return self.te_saved
+
+    def _record(self, rec: dict):
+        self.records.append(rec)
+
+    # ------------------------------------------------------------------ backward construction
+    def _btmp(self, name: str, numel: int, dtype=torch.float16) -> torch.Tensor:
+        """shared backward scratch (sized for the largest request)."""
+        key = f"train/{self.b}x{self.h}x{self.w}/bwd/{name}"
+        t = self.eng.arena.bufs.get(key)
+        if t is not None and t.numel() >= numel and t.dtype == dtype:
+            return t[:numel]
+        self._bwd_sizes[(key, dtype)] = max(self._bwd_sizes.get((key, dtype), 0), numel)
+        return None
+
+    def _bemit(self, name: str, meta: dict, fn: Callable[[int], None]):
+        self.bwd_ops.append(fn)
+        self.bwd_info.append((name, meta))
+
+    def _build_backward(self):
+        # pass 1 sizes the shared scratch buffers, pass 2 emits the ops (same trick as the forward)
+        self._bwd_sizes: Dict[Tuple[str, torch.dtype], int] = {}
+        self._sizing = True
+        self._emit_backward()
+        for (key, dtype), numel in self._bwd_sizes.items():
+            self.eng.arena.get(key, numel, dtype)
+        self._sizing = False
+        self.bwd_ops, self.bwd_info = [], []
+        self._emit_backward()
+
+    # gradient buffer of an activation tensor + whether something has been written to it yet (in backward order)
+    def _grad_buf(self, t: torch.Tensor) -> Tuple[torch.Tensor, bool]:
+        key = t.data_ptr()
+        g = self._gbuf.get(key)
+        if g is None:
+            self._uid += 1
+            g = self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/grad{len(self._gbuf)}", t.numel(), torch.float16)
+            self._gbuf[key] = g
+            self._gwritten[key] = False
+        w = self._gwritten[key]
+        self._gwritten[key] = True
+        return g, w
+
+    def _grad_ready(self, t: torch.Tensor) -> torch.Tensor:
+        key = t.data_ptr()
+        assert self._gwritten.get(key, False), "backward order error: gradient consumed before it was produced"
+        return self._gbuf[key]
+
+    # ---- op helpers (each appends to bwd_ops; in the sizing pass buffers may be None and nothing is emitted)
+    def _colsum_to(self, x: torch.Tensor, rows: int, c: int, total, total2=None, scaled=True):
+        lib = self.lib
+        parts = max(1, min(148 * 4, -(-rows // 64)))
+        partial = self._btmp("colsum_partial", parts * c, torch.float32)
+        if self._sizing:
+            return
+        inv = self.inv_scale_ptr if scaled else None
+        a1 = (x.data_ptr(), rows, c, partial.data_ptr(), parts)
+        a2 = (partial.data_ptr(), 1, parts, c, None, 0, 0, inv, _p(total), _p(total2))
+
+        def run(st):
+            check(lib.dsg_colsum_h16(*a1, st), "colsum_h16")
+            check(lib.dsg_colsum_finalize(*a2, st), "colsum_finalize")
+        self._bemit("colsum", {"bytes": rows * c * 2}, run)
+
+    def _wgrad(self, mode, x, dy, hw, cin, cout, grad, ci_total=None, ci_off=0):
+        lib = self.lib
+        nbytes = max(16, int(lib.dsg_wgrad_workspace_bytes(mode, self.b, hw[0], hw[1], cin, cout)))
+        ws = self._btmp("wgrad_ws", (nbytes + 3) // 4, torch.float32)
+        if self._sizing:
+            return
+        a = WgradArgs()
+        a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, self.b, hw[0], hw[1], cin, cout
+        a.x, a.dy, a.grad = x.data_ptr(), dy.data_ptr(), grad.data_ptr()
+        a.ci_total, a.ci_off, a.accumulate = (ci_total or cin), ci_off, 0
+        a.inv_scale = self.inv_scale_ptr
+        a.workspace, a.workspace_bytes, a.impl = ws.data_ptr(), ws.numel() * 4, 0
+        self.keep.append(a)
+        ref = C.byref(a)
+        opx = {0: hw[0] * hw[1], 1: hw[0] * hw[1] // 4, 2: hw[0] * hw[1] * 4, 3: hw[0] * hw[1]}[mode]
+        kk = 1 if mode == 3 else 9
+        self._bemit("wgrad", {"flops": 2 * self.b * opx * cout * cin * kk, "mode": mode, "hw": hw, "cin": cin,
+                              "cout": cout}, lambda st, r=ref: check(lib.dsg_conv_wgrad(r, st), "conv_wgrad"))
+
+    def _dgrad(self, run_mode, dy, hw_in, cin, cout, wname, out, residual=None, flops_k=None):
+        """conv over the gradient dy ([b, hw_in, cin]) with dgrad-packed weights -> out ([.., cout])."""
+        if self._sizing:
+            return
+        eng, lib = self.eng, self.lib
+        a = ConvArgs()
+        a.mode, a.n, a.h, a.w, a.cin, a.cout = run_mode, self.b, hw_in[0], hw_in[1], cin, cout
+        a.x = dy.data_ptr()
+        a.wpacked = eng.weights[wname].data_ptr()
+        a.residual = _p(residual)
+        a.out = out.data_ptr()
+        a.impl = eng.conv_impl
+        self.keep.append(a)
+        ref = C.byref(a)
+        self._bemit("dgrad", {"flops": flops_k, "mode": run_mode, "hw": hw_in, "cin": cin, "cout": cout},
+                    lambda st, r=ref: check(lib.dsg_conv(r, st), f"dgrad {wname}"))
+
+    def _gn_bwd(self, dy, x1, c1, st1, x2, c2, st2, gname, bname, act, hw, addend, dx1, acc1, dx2, acc2,
+                g_gamma, g_beta, colsum_to=None):
+        """colsum_to = (per_n tensor, stride, offset, total tensor) or None."""
+        eng, lib, b = self.eng, self.lib, self.b
+        c, npx = c1 + c2, hw[0] * hw[1]
+        chunks = max(1, min(64, (148 * 4) // b, -(-npx // 64)))
+        partial = self._btmp("gn_partial", b * chunks * c * 2, torch.float32)
+        parts = max(1, min((148 * 4) // b, -(-npx // 32))) if colsum_to else 0
+        colsum = self._btmp("gn_colsum", max(1, b * parts * c), torch.float32) if colsum_to else None
+        if self._sizing:
+            return
+        g, bt = eng.weights[gname], eng.weights[bname]
+        a1 = (dy.data_ptr(), x1.data_ptr(), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps,
+              act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1), _p(dx2), int(acc2), _p(colsum),
+              parts, b, npx, eng.groups)
+        a2 = (partial.data_ptr(), b * chunks, c, self.inv_scale_ptr, g_gamma.data_ptr(), g_beta.data_ptr())
+        a3 = None
+        if colsum_to:
+            per_n, stride, off, total = colsum_to
+            a3 = (colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr, _p(total), None)
+
+        def run(st):
+            check(lib.dsg_gn_bwd(*a1, st), "gn_bwd")
+            check(lib.dsg_gn_bwd_params(*a2, st), "gn_bwd_params")
+            if a3 is not None:
+                check(lib.dsg_colsum_finalize(*a3, st), "colsum_finalize")
+        nbytes = b * npx * c * 2
+        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0)}, run)
+
+    # ------------------------------------------------------------------ the backward program
+    def _emit_backward(self):
+        eng, lib, b = self.eng, self.lib, self.b
+        G = self.grads
+        self._gbuf: Dict[int, torch.Tensor] = {}
+        self._gwritten: Dict[int, bool] = {}
+        self.scale = eng.arena.get(f"train/{b}/scale", 2, torch.float32)
+        self.scale_ptr = self.scale.data_ptr()
+        self.inv_scale_ptr = self.scale.data_ptr() + 4
+        self.dtemb = eng.arena.get(f"train/{b}/dtemb", b * eng.proj_total, torch.float32)
+        for rec in reversed(self.records):
+            getattr(self, "_bwd_" + rec["kind"])(rec)
+        self._bwd_time_embed()
+
+    def _bwd_out(self, rec):
+        """conv_norm_out + SiLU + conv_out; entry point of the backward (sets the gradient scale)."""
+        eng, lib, b = self.eng, self.lib, self.b
+        W, G = eng.weights, self.grads
+        x, hw, act, c0 = rec["x"], rec["hw"], rec["act"], rec["c0"]
+        npx = hw[0] * hw[1]
+        numel = b * self.cout * npx
+        amax_parts = 148 * 4
+        amax_partial = self._btmp("amax_partial", amax_parts, torch.float32)
+        wt = self._btmp("conv_out_wt", c0 * self.cout * 9, torch.float32)
+        zero_b = self._btmp("zero_bias", c0, torch.float32)
+        dact = self._btmp("dact", b * npx * c0)
+        sw_parts = min(b * hw[0], 148 * 4)
+        sw_partial = self._btmp("small_wgrad_partial", sw_parts * (self.cout * 9 * c0 + self.cout), torch.float32)
+        gx, acc = self._grad_buf(x)
+        if not self._sizing:
+            zero_b.zero_()
+            w_out = W["conv_out.w"]
+
+            def run(st):
+                dout = self.dout_ptr
+                check(lib.dsg_grad_scale(dout, numel, amax_partial.data_ptr(), amax_parts, self.scale_ptr, st),
+                      "grad_scale")
+                check(lib.dsg_conv_out_dgrad_weight(w_out.data_ptr(), self.cout, c0, self.scale_ptr, wt.data_ptr(), st),
+                      "conv_out_dgrad_weight")
+                check(lib.dsg_conv_in(dout, wt.data_ptr(), zero_b.data_ptr(), dact.data_ptr(), b, self.cout, hw[0],
+                                      hw[1], c0, st), "conv_out dgrad")
+                check(lib.dsg_small_wgrad(act.data_ptr(), dout, b, hw[0], hw[1], c0, self.cout, 1,
+                                          sw_partial.data_ptr(), sw_parts, None, G["conv_out.weight"].data_ptr(),
+                                          G["conv_out.bias"].data_ptr(), st), "conv_out wgrad")
+            self._bemit("conv_out_bwd", {"bytes": b * npx * (self.cout * 4 * 2 + c0 * 2 * 2)}, run)
+        self._gn_bwd(dact, x, c0, rec["st1"], None, 0, None, "norm_out.g", "norm_out.b", 1, hw, None, gx, acc, None, 0,
+                     G["conv_norm_out.weight"], G["conv_norm_out.bias"])
+
+    def _bwd_in(self, rec):
+        """conv_in: weight / bias gradient only (the input image needs no gradient)."""
+        lib, b = self.lib, self.b
+        G = self.grads
+        out, hw, c0 = rec["out"], rec["hw"], rec["c0"]
+        g = self._grad_ready(out)
+        self._colsum_to(g, b * hw[0] * hw[1], c0, G["conv_in.bias"])
+        sw_parts = min(b * hw[0], 148 * 4)
+        sw_partial = self._btmp("small_wgrad_partial", sw_parts * (self.cin * 9 * c0 + self.cin), torch.float32)
+        if self._sizing:
+            return
+
+        def run(st):
+            check(lib.dsg_small_wgrad(g.data_ptr(), self.in_ptr, b, hw[0], hw[1], c0, self.cin, 0, sw_partial.data_ptr(),
+                                      sw_parts, self.inv_scale_ptr, G["conv_in.weight"].data_ptr(), None, st),
+                  "conv_in wgrad")
+        self._bemit("conv_in_bwd", {"bytes": b * hw[0] * hw[1] * (c0 * 2 + self.cin * 4)}, run)
+
+    def _bwd_resnet(self, rec):
+        eng, b = self.eng, self.b
+        G = self.grads
+        r, x1, x2, hw, out = rec["r"], rec["x1"], rec["x2"], rec["hw"], rec["out"]
+        c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
+        c, npx = c1 + c2, hw[0] * hw[1]
+        g_out = self._grad_ready(out)
+        # conv2 (+ shortcut): bias, weights
+        self._colsum_to(g_out, b * npx, co, G[f"{pre}.conv2.bias"],
+                        G[f"{pre}.conv_shortcut.bias"] if r["has_sc"] else None)
+        self._wgrad(0, rec["a2"], g_out, hw, co, co, G[f"{pre}.conv2.weight"])
+        if r["has_sc"]:
+            self._wgrad(3, x1, g_out, hw, c1, co, G[f"{pre}.conv_shortcut.weight"], ci_total=c, ci_off=0)
+            if x2 is not None:
+                self._wgrad(3, x2, g_out, hw, c2, co, G[f"{pre}.conv_shortcut.weight"], ci_total=c, ci_off=c1)
+        # conv2 data gradient -> GroupNorm2 + SiLU backward -> dh (+ time-embedding / conv1 bias gradients)
+        dact = self._btmp("dact", b * npx * max(co, c))
+        dh = self._btmp("dh", b * npx * co)
+        self._dgrad(0, g_out, hw, co, co, f"{pre}.conv2.dg", dact, flops_k=2 * b * npx * co * co * 9)
+        self._gn_bwd(dact, rec["h"], co, rec["h_stats"], None, 0, None, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, hw, None,
+                     dh, 0, None, 0, G[f"{pre}.norm2.weight"], G[f"{pre}.norm2.bias"],
+                     colsum_to=(self.dtemb, eng.proj_total, r["temb_off"], G[f"{pre}.conv1.bias"]))
+        # conv1: weights, data gradient
+        self._wgrad(0, rec["a1"], dh, hw, c, co, G[f"{pre}.conv1.weight"])
+        self._dgrad(0, dh, hw, co, c, f"{pre}.conv1.dg", dact, flops_k=2 * b * npx * co * c * 9)
+        # shortcut gradient w.r.t. cat(x1, x2): 1x1 conv transpose, or the identity
+        if r["has_sc"]:
+            dsc = self._btmp("dsc", b * npx * c)
+            self._dgrad(3, g_out, hw, co, c, f"{pre}.sc.dg", dsc, flops_k=2 * b * npx * co * c)
+            addend = dsc
+        else:
+            assert x2 is None and c1 == co
+            addend = g_out
+        gx1, acc1 = self._grad_buf(x1)
+        gx2, acc2 = self._grad_buf(x2) if x2 is not None else (None, False)
+        self._gn_bwd(dact, x1, c1, rec["st1"], x2, c2, rec["st2"], f"{pre}.norm1.g", f"{pre}.norm1.b", 1, hw, addend,
+                     gx1, acc1, gx2, acc2, G[f"{pre}.norm1.weight"], G[f"{pre}.norm1.bias"])
+
+    def _bwd_attn(self, rec):
+        eng, lib, b = self.eng, self.lib, self.b
+        G = self.grads
+        a, x, hw, out = rec["a"], rec["x"], rec["hw"], rec["out"]
+        ch, pre, hd = a["ch"], a["prefix"], a["head_dim"]
+        npx = hw[0] * hw[1]
+        g_out = self._grad_ready(out)
+        # to_out: bias, weight, data gradient
+        self._colsum_to(g_out, b * npx, ch, G[f"{pre}.to_out.0.bias"])
+        self._wgrad(3, rec["o"], g_out, hw, ch, ch, G[f"{pre}.to_out.0.weight"])
+        do = self._btmp("attn_do", b * npx * ch)
+        self._dgrad(3, g_out, hw, ch, ch, f"{pre}.out.dg", do, flops_k=2 * b * npx * ch * ch)
+        # attention core
+        dqkv = self._btmp("attn_dqkv", b * npx * 3 * ch)
+        heads = ch // hd
+        aws = self._btmp("attn_ws", 2 * b * heads * npx, torch.float32)
+        if not self._sizing:
+            args = (rec["qkv"].data_ptr(), rec["o"].data_ptr(), do.data_ptr(), dqkv.data_ptr(), aws.data_ptr(), b, npx,
+                    heads, hd)
+            self._bemit("attention_bwd", {"flops": 10 * b * npx * npx * ch},
+                        lambda st: check(lib.dsg_attention_bwd(*args, st), "attention_bwd"))
+        # q/k/v projections: the fused [3c] gradient is scattered to the three parameter pairs
+        qkv_b = self._btmp("attn_qkv_bias", 3 * ch, torch.float32)
+        qkv_w = self._btmp("attn_qkv_w", 3 * ch * ch, torch.float32)
+        self._colsum_to(dqkv, b * npx, 3 * ch, qkv_b)
+        self._wgrad(3, rec["act"], dqkv, hw, ch, 3 * ch, qkv_w)
+        if not self._sizing:
+            dst = [(G[f"{pre}.to_{n}.weight"], G[f"{pre}.to_{n}.bias"]) for n in "qkv"]
+
+            def scatter(st):
+                for i, (gw, gb) in enumerate(dst):
+                    gw.view(-1).copy_(qkv_w[i * ch * ch:(i + 1) * ch * ch])
+                    gb.copy_(qkv_b[i * ch:(i + 1) * ch])
+            self._bemit("qkv_scatter", {}, scatter)
+        da = self._btmp("dact", b * npx * ch)
+        self._dgrad(3, dqkv, hw, 3 * ch, ch, f"{pre}.qkv.dg", da, flops_k=2 * b * npx * 3 * ch * ch)
+        gx, acc = self._grad_buf(x)
+        self._gn_bwd(da, x, ch, rec["st1"], None, 0, None, f"{pre}.gn.g", f"{pre}.gn.b", 0, hw, g_out, gx, acc, None, 0,
+                     G[f"{pre}.group_norm.weight"], G[f"{pre}.group_norm.bias"])
+
+    def _bwd_down(self, rec):
+        """Downsample2D conv (3x3 stride 2)."""
+        b = self.b
+        G = self.grads
+        pre, x, hw, out, ch = rec["prefix"], rec["x"], rec["hw"], rec["out"], rec["ch"]
+        ohw = (hw[0] // 2, hw[1] // 2)
+        g_out = self._grad_ready(out)
+        self._colsum_to(g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
+        self._wgrad(1, x, g_out, hw, ch, ch, G[pre + ".weight"])
+        gx, acc = self._grad_buf(x)
+        # transpose of the stride-2 conv = a four-phase sub-pixel conv over the low-resolution gradient
+        self._dgrad(2, g_out, ohw, ch, ch, pre + ".dg", gx, residual=gx if acc else None,
+                    flops_k=2 * b * ohw[0] * ohw[1] * ch * ch * 9)
+
+    def _bwd_up(self, rec):
+        """Upsample2D (nearest 2x + 3x3 conv)."""
+        b = self.b
+        G = self.grads
+        pre, x, hw, out, ch = rec["prefix"], rec["x"], rec["hw"], rec["out"], rec["ch"]
+        ohw = (hw[0] * 2, hw[1] * 2)
+        g_out = self._grad_ready(out)
+        self._colsum_to(g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
+        self._wgrad(2, x, g_out, hw, ch, ch, G[pre + ".weight"])
+        gx, acc = self._grad_buf(x)
+        self._dgrad(4, g_out, ohw, ch, ch, pre + ".dg", gx, residual=gx if acc else None,
+                    flops_k=2 * b * ohw[0] * ohw[1] * ch * ch * 9)
+
+    def _bwd_time_embed(self):
+        """Timesteps -> linear_1 -> SiLU -> linear_2 -> SiLU -> every ResnetBlock's time_emb_proj."""
+        eng, lib, b = self.eng, self.lib, self.b
+        G, W = self.grads, eng.weights
+        hid, P = eng.temb_hidden, eng.proj_total
+        in_dim = eng.time_dim
+        d_pre2 = self._btmp("te_dpre2", b * hid, torch.float32)
+        d_pre1 = self._btmp("te_dpre1", b * hid, torch.float32)
+        if self._sizing:
+            return
+        sv = self.te_saved
+        e_ptr = sv.data_ptr()
+        pre1_ptr = e_ptr + 4 * b * in_dim
+        h1s_ptr = pre1_ptr + 4 * b * hid
+        pre2_ptr = h1s_ptr + 4 * b * hid
+        inv = self.inv_scale_ptr
+        dt = self.dtemb.data_ptr()
+        semb = self.emb_ws.data_ptr()
+        proj = [(r["temb_off"], r["cout"], G[r["prefix"] + ".time_emb_proj.weight"].data_ptr(),
+                 G[r["prefix"] + ".time_emb_proj.bias"].data_ptr()) for r in eng.resnets]
+        w2 = W["te.linear_2.w_oi"].data_ptr()
+        wp = W["te.proj.w"].data_ptr()
+        g1w, g1b = G["time_embedding.linear_1.weight"].data_ptr(), G["time_embedding.linear_1.bias"].data_ptr()
+        g2w, g2b = G["time_embedding.linear_2.weight"].data_ptr(), G["time_embedding.linear_2.bias"].data_ptr()
+
+        def run(st):
+            for off, co, gw, gb in proj:
+                check(lib.dsg_lin_wgrad_small(dt, P, off, semb, hid, co, hid, b, inv, gw, gb, st), "time_emb_proj wgrad")
+            check(lib.dsg_lin_dgrad_small(dt, P, 0, wp, P, hid, pre2_ptr, d_pre2.data_ptr(), b, st), "temb dgrad 2")
+            check(lib.dsg_lin_wgrad_small(d_pre2.data_ptr(), hid, 0, h1s_ptr, hid, hid, hid, b, inv, g2w, g2b, st),
+                  "linear_2 wgrad")
+            check(lib.dsg_lin_dgrad_small(d_pre2.data_ptr(), hid, 0, w2, hid, hid, pre1_ptr, d_pre1.data_ptr(), b, st),
+                  "temb dgrad 1")
+            check(lib.dsg_lin_wgrad_small(d_pre1.data_ptr(), hid, 0, e_ptr, in_dim, hid, in_dim, b, inv, g1w, g1b, st),
+                  "linear_1 wgrad")
+        self._bemit("time_embed_bwd", {}, run)
+
+    # ------------------------------------------------------------------ execution
+    def backward(self, dout: torch.Tensor, sample: torch.Tensor):
+        """dout: fp32 NCHW gradient of the model output; sample: the forward's fp32 NCHW input (conv_in's wgrad)."""
+        assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.is_cuda
+        self.dout_ptr = C.c_void_p(dout.data_ptr())
+        self.in_ptr = C.c_void_p(sample.data_ptr())
+        st = torch.cuda.current_stream(dout.device).cuda_stream
+        for op in self.bwd_ops:
+            op(st)
+
+    def backward_timed(self, dout: torch.Tensor, sample: torch.Tensor):
+        dev = dout.device
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.bwd_ops) + 1)]
+        stream = torch.cuda.current_stream(dev)
+        ops = self.bwd_ops
+        hooked = []
+        for i, op in enumerate(ops):
+            def h(st, op=op, i=i):
+                op(st)
+                evs[i + 1].record(stream)
+            hooked.append(h)
+        self.bwd_ops = hooked
+        try:
+            evs[0].record(stream)
+            self.backward(dout, sample)
+        finally:
+            self.bwd_ops = ops
+        torch.cuda.synchronize(dev)
+        return [(n, m, evs[i].elapsed_time(evs[i + 1])) for i, (n, m) in enumerate(self.bwd_info)]

@@ -192,15 +192,20 @@ class UNet2DModel(nn.Module, ConfigMixin):
 
     # ------------------------------------------------------------------ engine management
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # _weights_epoch: bumped by optimizers that update the parameters behind autograd's back (fused AdamW kernel)
+        return (getattr(self, "_weights_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def engine(self) -> UNetEngine:
-        """The CUDA engine with weights packed from the CURRENT parameter values (re-packed when they change)."""
+    def engine(self, train: bool = False) -> UNetEngine:
+        """The CUDA engine with weights packed from the CURRENT parameter values (re-packed when they change).
+        train=True also packs the data-gradient forms of the conv weights (and keeps doing so from then on)."""
         dev = self.device
         if dev.type != "cuda":
             raise DsgError("UNet2DModel is on the CPU: move it to a B200 (`.to('cuda')`); dsg_b200 has no CPU path")
         if self._engine is None or self._engine.device != dev:
             self._engine = UNetEngine(dict(self.config), dev)
+            self._engine_key = None
+        if train and not self._engine.train_packs:
+            self._engine.train_packs = True
             self._engine_key = None
         key = self._weights_key()
         if key != self._engine_key:

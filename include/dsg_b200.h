@@ -166,8 +166,9 @@ int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t tokens, int3
  * partial: float[parts] scratch. */
 int dsg_grad_scale(const float* dout, int64_t numel, float* partial, int32_t parts, float* scale, void* stream);
 
-/* same as dsg_time_embed; saved (may be NULL): float[batch][2*half + 3*hidden] = per sample
- * [ sinusoid | pre-activation of linear_1 | SiLU of it | pre-activation of linear_2 ] for the backward. */
+/* same as dsg_time_embed; saved (may be NULL): float[batch * (2*half + 3*hidden)] = four dense arrays for the
+ * backward: sinusoid [batch][2*half], then [batch][hidden] each of the pre-activation of linear_1, SiLU of it, and
+ * the pre-activation of linear_2. */
 int dsg_time_embed_ex(const float* t, const float* freqs, int32_t half, int32_t flip_sin_to_cos, const float* w1t,
                       const float* b1, const float* w2t, const float* b2, int32_t hidden, const float* wp,
                       const float* bp, int32_t proj_total, float* emb_ws, float* out, int32_t batch, float* saved,
