@@ -50,6 +50,8 @@ class AcceleratedOptimizer:
         acc = self.accelerator
         if not acc.sync_gradients:
             return
+        if closure is None and acc._fused_adamw_step(self):
+            return
         if acc.scaler is not None:
             before = acc.scaler.get_scale()
             acc.scaler.step(self.optimizer, closure) if closure is not None else acc.scaler.step(self.optimizer)
@@ -164,6 +166,10 @@ class Accelerator:
         self._models: List[torch.nn.Module] = []
         self._optimizers: List[AcceleratedOptimizer] = []
         self._flat_grad: Optional[torch.Tensor] = None
+        self._fused_state = {}
+        self._ctl = None
+        self._scale_host: Optional[float] = None
+        self._growth_tracker = 0
         self.trackers = []
         self._writer = None
 
@@ -240,8 +246,117 @@ class Accelerator:
             # replicas start identical: broadcast rank 0's parameters/buffers once
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src=0)
+        if self.device.type == "cuda" and hasattr(model, "engine"):
+            self._flatten_parameters(model)
         self._models.append(model)
         return model
+
+    # ------------------------------------------------------------------ flat buffers + fused optimizer (CUDA engine)
+    @staticmethod
+    def _flatten_parameters(model: torch.nn.Module):
+        """Re-home every parameter in ONE flat fp32 buffer (same Parameter objects, same values): the fused AdamW
+        kernel and the single gradient all-reduce then work on whole buffers instead of 160 small tensors."""
+        params = list(model.parameters())
+        if not params or getattr(model, "_flat_params", None) is not None:
+            return
+        if any(p.dtype != torch.float32 for p in params):
+            return
+        total = sum(p.numel() for p in params)
+        flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+        model._flat_params = flat
+
+    def _flat_grad_of(self, model) -> Optional[torch.Tensor]:
+        """the flat gradient buffer the engine's last backward wrote, if the parameters' .grad alias it."""
+        fg = getattr(model, "_flat_grads", None)
+        if fg is None:
+            return None
+        flat = fg.flat[fg.last]
+        first, last = fg.params[0].grad, fg.params[-1].grad
+        if first is None or last is None:
+            return None
+        if first.data_ptr() != flat.data_ptr():
+            return None
+        if last.data_ptr() != flat.data_ptr() + 4 * (flat.numel() - last.numel()):
+            return None
+        return flat
+
+    def _loss_scale_value(self) -> float:
+        if self.scaler is None:
+            return 1.0
+        if self._scale_host is None:
+            self._scale_host = float(self.scaler.get_scale())
+        return self._scale_host
+
+    def _fused_grad_norm(self, model, max_norm: float) -> Optional[torch.Tensor]:
+        flat_g = self._flat_grad_of(model)
+        if flat_g is None:
+            return None
+        from .. import ops
+        ctl = ops.grad_norm(flat_g, 1.0 / self._loss_scale_value(), float(max_norm))
+        self._ctl = (model, flat_g.data_ptr(), ctl)
+        return ctl
+
+    def _fused_adamw_step(self, wrapped: "AcceleratedOptimizer") -> bool:
+        """clip + unscale + AdamW in one pass over the flat buffers (dsg_adamw_step); False = not applicable."""
+        opt = wrapped.optimizer
+        if type(opt) is not torch.optim.AdamW or len(opt.param_groups) != 1 or len(self._models) != 1:
+            return False
+        model = self._models[0]
+        flat_p = getattr(model, "_flat_params", None)
+        grp = opt.param_groups[0]
+        if flat_p is None or grp.get("amsgrad") or grp.get("maximize") or grp.get("capturable") \
+                or grp.get("differentiable"):
+            return False
+        fg = getattr(model, "_flat_grads", None)
+        if fg is None or len(grp["params"]) != len(fg.params) or any(a is not b for a, b in zip(grp["params"], fg.params)):
+            return False
+        if fg.params[0].data_ptr() != flat_p.data_ptr():
+            return False
+        flat_g = self._flat_grad_of(model)
+        if flat_g is None:
+            return False
+        ctl = None
+        if self._ctl is not None and self._ctl[0] is model and self._ctl[1] == flat_g.data_ptr():
+            ctl = self._ctl[2]
+        if ctl is None:
+            ctl = self._fused_grad_norm(model, 0.0)
+        self._ctl = None
+        st = self._fused_state.get(id(opt))
+        if st is None:
+            st = {"m": torch.zeros_like(flat_p), "v": torch.zeros_like(flat_p), "step": 0}
+            self._fused_state[id(opt)] = st
+        from .. import ops
+        lr = grp["lr"]
+        lr = float(lr.item()) if torch.is_tensor(lr) else float(lr)
+        b1, b2 = grp["betas"]
+        # one host read per step (the step was skipped iff the gradients were not finite): GradScaler bookkeeping
+        skipped = bool(ctl[2].item() != 0.0)
+        if not skipped:
+            st["step"] += 1
+            ops.adamw_step(flat_p, flat_g, st["m"], st["v"], lr, float(b1), float(b2), float(grp["eps"]),
+                           float(grp["weight_decay"]), st["step"], ctl)
+            model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1
+        wrapped.step_was_skipped = skipped
+        if self.scaler is not None:
+            scale = self._loss_scale_value()
+            if skipped:
+                scale *= self.scaler.get_backoff_factor()
+                self._growth_tracker = 0
+            else:
+                self._growth_tracker += 1
+                if self._growth_tracker >= self.scaler.get_growth_interval():
+                    scale *= self.scaler.get_growth_factor()
+                    self._growth_tracker = 0
+            if scale != self._scale_host:
+                self.scaler.update(new_scale=scale)
+                self._scale_host = scale
+        return True
 
     def unwrap_model(self, model, keep_fp32_wrapper: bool = True):
         return model
@@ -264,6 +379,12 @@ class Accelerator:
 
     def _allreduce_grads(self):
         """ONE all-reduce over a single flat gradient buffer, averaged over ranks."""
+        if len(self._models) == 1:
+            flat = self._flat_grad_of(self._models[0])
+            if flat is not None:   # the engine's backward already wrote one flat buffer: reduce it in place
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                flat.mul_(1.0 / self.num_processes)
+                return
         params = [p for m in self._models for p in m.parameters() if p.grad is not None]
         if not params:
             return
@@ -297,6 +418,18 @@ class Accelerator:
                 self.scaler.unscale_(o.optimizer)
 
     def clip_grad_norm_(self, parameters: Iterable[torch.Tensor], max_norm: float, norm_type: float = 2):
+        if norm_type == 2 and len(self._models) == 1 and len(self._optimizers) == 1 \
+                and type(self._optimizers[0].optimizer) is torch.optim.AdamW \
+                and getattr(self._models[0], "_flat_params", None) is not None:
+            # CUDA engine: the norm of the flat gradient buffer; unscale + clip are applied inside the fused AdamW
+            # kernel (the .grad tensors keep their scaled values)
+            plist = list(parameters)
+            fg = getattr(self._models[0], "_flat_grads", None)
+            if fg is not None and len(plist) == len(fg.params) and all(a is b for a, b in zip(plist, fg.params)):
+                ctl = self._fused_grad_norm(self._models[0], max_norm)
+                if ctl is not None:
+                    return ctl[0]
+            parameters = plist
         self.unscale_gradients()
         return torch.nn.utils.clip_grad_norm_(parameters, max_norm, norm_type=norm_type)
 

@@ -136,8 +136,14 @@ def test_pipeline_graph_vs_eager_vs_oracle(tmp_path):
     assert imgs[0].size == (64, 64)
 
 
-def test_training_path_raises_loudly():
+def test_grad_mode_forward_matches_inference_and_input_grad_raises():
+    """grad mode runs the training program (saved activations): same output as the inference program; gradients
+    w.r.t. the input image are not provided (the reference never asks for them) and raise instead of being wrong."""
     _, model = _pair(C1_CFG)
     x = torch.randn(1, 3, 64, 64).cuda()
+    with torch.no_grad():
+        ref = model(x, 1).sample
+    out = model(x, 1).sample
+    assert out.requires_grad and torch.equal(out.detach(), ref)
     with pytest.raises(NotImplementedError):
-        model(x, 1)  # grad mode + trainable params: backward kernels are not built yet
+        model(x.clone().requires_grad_(True), 1)
