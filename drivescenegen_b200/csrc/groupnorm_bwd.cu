@@ -29,7 +29,7 @@ struct GnBwdArgs {
   const __half* x2; int c2; const long long* st2;
   const float* gamma; const float* beta;
   float eps; int act;
-  float* partial;     // [n][chunks][C][2]
+  float* partial;     // [n][chunks + 1][C][2]: chunk partials (sum g, sum g x), then the per-sample (A_c, B_c)
   int chunks;
   const __half* addend;  // optional [n][hw][C]
   __half* dx1; int acc1;
@@ -74,59 +74,60 @@ __device__ __forceinline__ float silu_grad_f(float y) {
   return sg * fmaf(y, 1.0f - sg, 1.0f);
 }
 
-__global__ void __launch_bounds__(GB_THREADS) gn_bwd_stats_kernel(const GnBwdArgs a) {
+// Pass 1.  Per (sample, pixel chunk, channel): sum g and sum g * x (raw x: the centring is applied when the chunks are
+// combined, sum g * xh = rstd * (sum g x - mean * sum g), which keeps the per-thread state small).
+constexpr int GB_ILP = 4;
+__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwdArgs a) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
   const int n = blockIdx.y, chunk = blockIdx.x;
   __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS];
   __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
   __shared__ float s_part[2][GB_THREADS * 8];
-  gn_moments(a, n, s_mean, s_rstd, s_t);
   const bool active = (int)threadIdx.x < ppi * V;
+  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  const int ch0 = v << 3;
+  const bool from1 = ch0 < a.c1;
+  const __half* src = from1 ? a.x1 : a.x2;
+  const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
+  const int64_t base_px = (int64_t)n * a.hw;
+  const int64_t p_begin = (int64_t)chunk * a.px_per_block;
+  int64_t p_end = p_begin + a.px_per_block;
+  if (p_end > a.hw) p_end = a.hw;
+  int64_t p = p_begin + prow;
+  gn_moments(a, n, s_mean, s_rstd, s_t);
   if (active) {
-    const int v = threadIdx.x % V, prow = threadIdx.x / V;
-    const int ch0 = v << 3;
-    const bool from1 = ch0 < a.c1;
-    const __half* src = from1 ? a.x1 : a.x2;
-    const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
-    float ga[8], yb[8], mu[8], rs[8], sA[8], sB[8];
+    float ga[8], yb[8], sA[8], sB[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = ch0 + j, g = ch / cpg;
-      mu[j] = s_mean[g]; rs[j] = s_rstd[g];
-      ga[j] = a.gamma[ch] * rs[j];
-      yb[j] = a.beta[ch] - mu[j] * ga[j];
+      ga[j] = a.gamma[ch] * s_rstd[g];
+      yb[j] = a.beta[ch] - s_mean[g] * ga[j];
       sA[j] = 0.f; sB[j] = 0.f;
     }
-    const int64_t base_px = (int64_t)n * a.hw;
-    const int64_t p_begin = (int64_t)chunk * a.px_per_block;
-    int64_t p_end = p_begin + a.px_per_block;
-    if (p_end > a.hw) p_end = a.hw;
-    for (int64_t p = p_begin + prow; p < p_end; p += 2 * ppi) {
-      const int64_t p2 = p + ppi;
-      const bool has2 = p2 < p_end;
-      const uint4 rx0 = ldg_nc_v4(src + (base_px + p) * cs + co);
-      const uint4 rd0 = ldg_nc_v4(a.dy + (base_px + p) * C + ch0);
-      uint4 rx1 = rx0, rd1 = rd0;
-      if (has2) {
-        rx1 = ldg_nc_v4(src + (base_px + p2) * cs + co);
-        rd1 = ldg_nc_v4(a.dy + (base_px + p2) * C + ch0);
-      }
-      float fx[8], fd[8];
-      unpack8(rx0, fx); unpack8(rd0, fd);
+    // GB_ILP pixels per iteration: all loads of an iteration are issued before the first use; two resident CTAs per SM
+    // keep ~64 KB in flight
+    for (; p < p_end; p += (int64_t)ppi * GB_ILP) {
+      uint4 rx[GB_ILP], rd[GB_ILP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
-        sA[j] += g;
-        sB[j] = fmaf(g, (fx[j] - mu[j]) * rs[j], sB[j]);
+      for (int u = 0; u < GB_ILP; ++u) {
+        const int64_t pp = p + (int64_t)u * ppi;
+        if (pp < p_end) {
+          rx[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+          rd[u] = ldg_nc_v4(a.dy + (base_px + pp) * C + ch0);
+        }
       }
-      if (has2) {
-        unpack8(rx1, fx); unpack8(rd1, fd);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
-          sA[j] += g;
-          sB[j] = fmaf(g, (fx[j] - mu[j]) * rs[j], sB[j]);
+      for (int u = 0; u < GB_ILP; ++u) {
+        if (p + (int64_t)u * ppi < p_end) {
+          float fx[8], fd[8];
+          unpack8(rx[u], fx); unpack8(rd[u], fd);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
+            sA[j] += g;
+            sB[j] = fmaf(g, fx[j], sB[j]);
+          }
         }
       }
     }
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_stats_kernel(const GnBwdArg
     }
   }
   __syncthreads();
-  float* o = a.partial + ((int64_t)n * a.chunks + chunk) * C * 2;
+  float* o = a.partial + ((int64_t)n * (a.chunks + 1) + chunk) * C * 2;
   for (int c = threadIdx.x; c < C; c += GB_THREADS) {
     float tA = 0.f, tB = 0.f;
     for (int r = 0; r < ppi; ++r) {  // fixed order
@@ -148,22 +149,41 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_stats_kernel(const GnBwdArg
   }
 }
 
-__global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+// Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1).
+__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
   const int n = blockIdx.y;
   __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS], s_m1[GB_MAX_GROUPS], s_m2[GB_MAX_GROUPS];
   __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
   __shared__ float s_part[2][GB_THREADS * 8];  // prologue: gamma * A / gamma * B per channel; epilogue: column sums
+  const bool active = (int)threadIdx.x < ppi * V;
+  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  const int ch0 = v << 3;
+  const bool from1 = ch0 < a.c1;
+  const __half* src = from1 ? a.x1 : a.x2;
+  __half* dst = from1 ? a.dx1 : a.dx2;
+  const int accum = from1 ? a.acc1 : a.acc2;
+  const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
+  const int64_t base_px = (int64_t)n * a.hw;
+  const int64_t p_begin = (int64_t)blockIdx.x * a.px_per_block;
+  int64_t p_end = p_begin + a.px_per_block;
+  if (p_end > a.hw) p_end = a.hw;
+  constexpr int ILP = 2;
+  int64_t p = p_begin + prow;
   gn_moments(a, n, s_mean, s_rstd, s_t);
   {
-    const float* pp = a.partial + (int64_t)n * a.chunks * C * 2;
+    const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
+    float* red = a.partial + ((int64_t)n * (a.chunks + 1) + a.chunks) * C * 2;  // per-sample (A_c, B_c) for the params
     for (int c = threadIdx.x; c < C; c += GB_THREADS) {
-      float tA = 0.f, tB = 0.f;
+      float tA = 0.f, tBx = 0.f;
       for (int k = 0; k < a.chunks; ++k) {  // fixed order
-        const float2 v = reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2)[c];
-        tA += v.x; tB += v.y;
+        const float2 t = reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2)[c];
+        tA += t.x; tBx += t.y;
       }
+      const int g = c / cpg;
+      const float tB = s_rstd[g] * (tBx - s_mean[g] * tA);  // sum g * xh
+      if (blockIdx.x == 0) reinterpret_cast<float2*>(red)[c] = make_float2(tA, tB);
       const float gm = a.gamma[c];
       s_part[0][c] = gm * tA;
       s_part[1][c] = gm * tB;
@@ -179,50 +199,49 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdArg
     }
     __syncthreads();
   }
-  const bool active = (int)threadIdx.x < ppi * V;
-  const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
-  const int ch0 = v << 3;
   float cs_acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cs_acc[j] = 0.f;
   if (active) {
-    const bool from1 = ch0 < a.c1;
-    const __half* src = from1 ? a.x1 : a.x2;
-    __half* dst = from1 ? a.dx1 : a.dx2;
-    const int accum = from1 ? a.acc1 : a.acc2;
-    const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
-    float ga[8], yb[8], mu[8], rs[8], k1[8], k2[8];
+    float ga[8], yb[8], pc[8], qc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = ch0 + j, g = ch / cpg;
-      mu[j] = s_mean[g]; rs[j] = s_rstd[g];
-      ga[j] = a.gamma[ch] * rs[j];
-      yb[j] = a.beta[ch] - mu[j] * ga[j];
-      k1[j] = rs[j] * s_m1[g];
-      k2[j] = rs[j] * s_m2[g];
+      const float mu = s_mean[g], rs = s_rstd[g];
+      ga[j] = a.gamma[ch] * rs;
+      yb[j] = a.beta[ch] - mu * ga[j];
+      pc[j] = -rs * rs * s_m2[g];
+      qc[j] = rs * (mu * rs * s_m2[g] - s_m1[g]);
     }
-    const int64_t base_px = (int64_t)n * a.hw;
-    const int64_t p_begin = (int64_t)blockIdx.x * a.px_per_block;
-    int64_t p_end = p_begin + a.px_per_block;
-    if (p_end > a.hw) p_end = a.hw;
-    for (int64_t p = p_begin + prow; p < p_end; p += ppi) {
-      const uint4 rx = ldg_nc_v4(src + (base_px + p) * cs + co);
-      const uint4 rd = ldg_nc_v4(a.dy + (base_px + p) * C + ch0);
-      uint4 ra = make_uint4(0, 0, 0, 0), ro = make_uint4(0, 0, 0, 0);
-      if (a.addend) ra = ldg_nc_v4(a.addend + (base_px + p) * C + ch0);
-      if (accum) ro = *reinterpret_cast<const uint4*>(dst + (base_px + p) * cs + co);
-      float fx[8], fd[8], fa[8], fo[8], r[8];
-      unpack8(rx, fx); unpack8(rd, fd); unpack8(ra, fa); unpack8(ro, fo);
+    for (; p < p_end; p += (int64_t)ppi * ILP) {
+      uint4 rx[ILP], rd[ILP], ra[ILP], ro[ILP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
-        const float xh = (fx[j] - mu[j]) * rs[j];
-        float d = fmaf(ga[j], g, -k1[j]);
-        d = fmaf(-xh, k2[j], d);
-        cs_acc[j] += d;
-        r[j] = (d + fa[j]) + fo[j];
+      for (int u = 0; u < ILP; ++u) {
+        ra[u] = make_uint4(0, 0, 0, 0); ro[u] = make_uint4(0, 0, 0, 0);
+        const int64_t pp = p + (int64_t)u * ppi;
+        if (pp < p_end) {
+          rx[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
+          rd[u] = ldg_nc_v4(a.dy + (base_px + pp) * C + ch0);
+          if (a.addend) ra[u] = ldg_nc_v4(a.addend + (base_px + pp) * C + ch0);
+          if (accum) ro[u] = *reinterpret_cast<const uint4*>(dst + (base_px + pp) * cs + co);
+        }
       }
-      stg_v4(dst + (base_px + p) * cs + co, pack8(r));
+#pragma unroll
+      for (int u = 0; u < ILP; ++u) {
+        const int64_t pp = p + (int64_t)u * ppi;
+        if (pp < p_end) {
+          float fx[8], fd[8], fa[8], fo[8], r[8];
+          unpack8(rx[u], fx); unpack8(rd[u], fd); unpack8(ra[u], fa); unpack8(ro[u], fo);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
+            const float d = fmaf(ga[j], g, fmaf(pc[j], fx[j], qc[j]));
+            cs_acc[j] += d;
+            r[j] = (d + fa[j]) + fo[j];
+          }
+          stg_v4(dst + (base_px + pp) * cs + co, pack8(r));
+        }
+      }
     }
   }
   if (a.colsum) {
@@ -241,15 +260,15 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdArg
   }
 }
 
-// d gamma / d beta: sum the per-(sample, chunk) partials in a fixed order, scale, store
-__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ partial, int rows, int C,
+// d gamma / d beta: sum the per-sample (A_c, B_c) slots (slot `chunks` of every sample) in a fixed order, scale, store
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ partial, int n, int chunks, int C,
                                                             const float* __restrict__ inv_scale,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float tA = 0.f, tB = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float2 v = reinterpret_cast<const float2*>(partial + (int64_t)r * C * 2)[c];
+  for (int i = 0; i < n; ++i) {
+    const float2 v = reinterpret_cast<const float2*>(partial + ((int64_t)i * (chunks + 1) + chunks) * C * 2)[c];
     tA += v.x; tB += v.y;
   }
   const float s = inv_scale ? *inv_scale : 1.0f;
@@ -361,10 +380,11 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   return DSG_OK;
 }
 
-int dsg_gn_bwd_params(const float* partial, int32_t rows, int32_t c, const float* inv_scale, float* dgamma,
-                      float* dbeta, void* stream) {
-  DSG_CHECK_ARG(partial && dgamma && dbeta && rows >= 0 && c > 0, "dsg_gn_bwd_params: bad args");
-  gn_bwd_params_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, rows, c, inv_scale, dgamma, dbeta);
+int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c, const float* inv_scale,
+                      float* dgamma, float* dbeta, void* stream) {
+  DSG_CHECK_ARG(partial && dgamma && dbeta && n >= 0 && chunks >= 1 && c > 0, "dsg_gn_bwd_params: bad args");
+  gn_bwd_params_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, n, chunks, c, inv_scale, dgamma,
+                                                                          dbeta);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd_params");
   return DSG_OK;
 }

@@ -157,7 +157,7 @@ class TrainProgram(_Program):
         eng, lib, b = self.eng, self.lib, self.b
         c, npx = c1 + c2, hw[0] * hw[1]
         chunks = max(1, min(64, (148 * 4) // b, -(-npx // 64)))
-        partial = self._btmp("gn_partial", b * chunks * c * 2, torch.float32)
+        partial = self._btmp("gn_partial", b * (chunks + 1) * c * 2, torch.float32)
         parts = max(1, min((148 * 4) // b, -(-npx // 32))) if colsum_to else 0
         colsum = self._btmp("gn_colsum", max(1, b * parts * c), torch.float32) if colsum_to else None
         if self._sizing:
@@ -166,7 +166,7 @@ class TrainProgram(_Program):
         a1 = (dy.data_ptr(), x1.data_ptr(), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps,
               act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1), _p(dx2), int(acc2), _p(colsum),
               parts, b, npx, eng.groups)
-        a2 = (partial.data_ptr(), b * chunks, c, self.inv_scale_ptr, g_gamma.data_ptr(), g_beta.data_ptr())
+        a2 = (partial.data_ptr(), b, chunks, c, self.inv_scale_ptr, g_gamma.data_ptr(), g_beta.data_ptr())
         a3 = None
         if colsum_to:
             per_n, stride, off, total = colsum_to

@@ -335,13 +335,17 @@ class Accelerator:
         lr = grp["lr"]
         lr = float(lr.item()) if torch.is_tensor(lr) else float(lr)
         b1, b2 = grp["betas"]
-        # one host read per step (the step was skipped iff the gradients were not finite): GradScaler bookkeeping
+        # The kernel itself skips the update when the gradients are not finite (ctl[2]); it is queued together with
+        # the re-pack of the fp16 weights for the next forward BEFORE the one host read of the step, so the GPU keeps
+        # working while the host waits for the flag (GradScaler / LR-scheduler bookkeeping needs it).
+        ops.adamw_step(flat_p, flat_g, st["m"], st["v"], lr, float(b1), float(b2), float(grp["eps"]),
+                       float(grp["weight_decay"]), st["step"] + 1, ctl)
+        model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1
+        if hasattr(model, "engine") and getattr(model, "_engine", None) is not None and model._engine.train_packs:
+            model.engine(train=True)
         skipped = bool(ctl[2].item() != 0.0)
         if not skipped:
             st["step"] += 1
-            ops.adamw_step(flat_p, flat_g, st["m"], st["v"], lr, float(b1), float(b2), float(grp["eps"]),
-                           float(grp["weight_decay"]), st["step"], ctl)
-            model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1
         wrapped.step_was_skipped = skipped
         if self.scaler is not None:
             scale = self._loss_scale_value()

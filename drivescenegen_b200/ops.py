@@ -222,7 +222,7 @@ def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
     if x2 is not None and stats2 is None:
         stats2 = gn_stats(x2)
     chunks = max(1, min(64, (148 * 4) // n, -(-hw // 64)))
-    partial = torch.empty((n, chunks, c, 2), dtype=torch.float32, device=dy.device)
+    partial = torch.empty((n, chunks + 1, c, 2), dtype=torch.float32, device=dy.device)
     if dx1 is None:
         dx1 = torch.empty_like(x1)
     if x2 is not None and dx2 is None:
@@ -234,7 +234,7 @@ def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
                          _p(dx2), int(acc2), _p(colsum), parts, n, hw, groups, _st(dy)), "gn_bwd")
     dgamma = torch.empty(c, dtype=torch.float32, device=dy.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=dy.device)
-    check(lib.dsg_gn_bwd_params(partial.data_ptr(), n * chunks, c, _p(inv_scale), dgamma.data_ptr(), dbeta.data_ptr(),
+    check(lib.dsg_gn_bwd_params(partial.data_ptr(), n, chunks, c, _p(inv_scale), dgamma.data_ptr(), dbeta.data_ptr(),
                                 _st(dy)), "gn_bwd_params")
     per_n = None
     if want_colsum:

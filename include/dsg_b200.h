@@ -183,8 +183,9 @@ int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
                         void* stream);
 
 /* GroupNorm(+SiLU) backward over cat(x1, x2) (see dsg_gn_apply for the forward and the statistics format).
- *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: float[n][chunks][c1+c2][2] scratch that
- *   afterwards holds the per-(sample, chunk) sums behind d beta / d gamma (dsg_gn_bwd_params), 1 <= chunks <= 64.
+ *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: float[n][chunks + 1][c1+c2][2] scratch
+ *   (chunk partials, then one slot per sample holding the sums behind d beta / d gamma, read by dsg_gn_bwd_params),
+ *   1 <= chunks <= 64.
  *   addend (may be NULL): h16 [n][hw][c1+c2] added to the input gradient (the ResnetBlock shortcut's gradient).
  *   dx1 / dx2: h16 gradients of x1 / x2; accN != 0 adds to the existing content (tensor with two consumers).
  *   colsum (may be NULL, then colsum_parts = 0): float[n][colsum_parts][c1+c2] receives per-CTA column sums of the
@@ -194,9 +195,9 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
                int32_t colsum_parts, int32_t n, int64_t hw, int32_t groups, void* stream);
-/* d gamma[c] / d beta[c] = inv_scale * sum over rows (= n * chunks) of partial[row][c][1 / 0] */
-int dsg_gn_bwd_params(const float* partial, int32_t rows, int32_t c, const float* inv_scale, float* dgamma,
-                      float* dbeta, void* stream);
+/* d gamma[c] / d beta[c] = inv_scale * sum over samples of the per-sample slot dsg_gn_bwd left in `partial` */
+int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c, const float* inv_scale,
+                      float* dgamma, float* dbeta, void* stream);
 /* column sums of an h16 [rows][c] tensor: partial float[parts][c] */
 int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32_t parts, void* stream);
 /* partial float[n][parts][c] -> per_n[i][per_n_off + c] (raw per-sample sums, may be NULL) and
