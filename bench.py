@@ -92,8 +92,20 @@ class ClockSampler:
         return out
 
 
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use every core the box gives us."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def oracle_steps_per_s(batch: int, size: int, steps: int, warmup: int):
     """CPU oracle: U-Net forward + DDPM step, fp32, all host threads."""
+    use_all_host_threads()
     from oracle.schedulers import OracleDDPMScheduler
     from oracle.unet import OracleUNet2D
     torch.manual_seed(0)
@@ -138,6 +150,7 @@ def oracle_train_steps_per_s(batch: int, size: int, steps: int):
     """CPU oracle: forward + autograd backward + torch AdamW, fp32, all host threads."""
     import torch.nn.functional as F
     from oracle.unet import OracleUNet2D
+    use_all_host_threads()
     torch.manual_seed(0)
     net = OracleUNet2D(sample_size=(size, size), **REF_CFG).train()
     opt = torch.optim.AdamW(net.parameters(), lr=1e-5)

@@ -95,7 +95,9 @@ SIGNATURES = {
     "dsg_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "dsg_conv_out_dgrad_weight": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),
     "dsg_small_wgrad": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
-    "dsg_attention_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dsg_attention_train_tc_ok": (C.c_int, [_i32, _i32]),
+    "dsg_attention_train": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
+    "dsg_attention_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "dsg_grad_norm": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _p, _p]),
     "dsg_adamw_step": (C.c_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _i32, _p, _p]),
 }

@@ -125,7 +125,25 @@ using namespace dsg;
 
 namespace dsg {
 int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int heads, int head_dim, float* dbg,
-                        cudaStream_t st);  // attention_tc.cu
+                        float* lse_out, cudaStream_t st);  // attention_tc.cu
+}
+
+extern "C" int dsg_attention_train_tc_ok(int32_t tokens, int32_t head_dim) {
+  return (head_dim == 8 && tokens % 128 == 0 && tokens >= 128 && tokens <= 2048) ? 1 : 0;
+}
+
+extern "C" int dsg_attention_train(const void* qkv, void* out, float* lse, int32_t n, int32_t tokens, int32_t heads,
+                                   int32_t head_dim, void* stream) {
+  DSG_CHECK_ARG(qkv && out && lse, "dsg_attention_train: null pointer");
+  DSG_CHECK_ARG(dsg_attention_train_tc_ok(tokens, head_dim), "dsg_attention_train: needs head_dim 8 and tokens a "
+                "multiple of 128 in [128, 2048] (use dsg_attention + dsg_attention_bwd with lse = NULL otherwise)");
+  DSG_CHECK_ARG(n >= 0 && n <= 65535 && heads > 0 && heads <= 65535, "dsg_attention_train: bad shape");
+  DSG_CHECK_ARG(((uintptr_t)qkv | (uintptr_t)out) % 16 == 0, "dsg_attention_train: pointers must be 16-byte aligned");
+  if (n == 0) return DSG_OK;
+  const int rc = launch_attention_tc((const __half*)qkv, (__half*)out, n, tokens, heads, head_dim, nullptr, lse,
+                                     (cudaStream_t)stream);
+  if (rc > 0) { dsg::set_error("dsg_attention_train: shape outside the tcgen05 kernel"); return DSG_ERR_UNSUPPORTED; }
+  return rc;
 }
 
 extern "C" int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t tokens, int32_t heads,
@@ -137,7 +155,7 @@ extern "C" int dsg_attention_ex(const void* qkv, void* out, int32_t n, int32_t t
   if (n == 0) return DSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (impl != 1) {
-    const int rc = launch_attention_tc((const __half*)qkv, (__half*)out, n, tokens, heads, head_dim, dbg, st);
+    const int rc = launch_attention_tc((const __half*)qkv, (__half*)out, n, tokens, heads, head_dim, dbg, nullptr, st);
     if (rc <= 0) return rc;
     if (impl == 2) {
       dsg::set_error("dsg_attention: the tcgen05 kernel needs head_dim 8 and 128 <= tokens <= 4096, tokens %% 128 == 0");

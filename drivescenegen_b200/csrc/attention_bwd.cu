@@ -214,27 +214,39 @@ __global__ void __launch_bounds__(AB_ROWS) attn_bwd_dq_kernel(const __half* __re
 
 using namespace dsg;
 
-extern "C" int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t n,
-                                 int32_t tokens, int32_t heads, int32_t head_dim, void* stream) {
-  DSG_CHECK_ARG(qkv && out && dout && dqkv && ws, "dsg_attention_bwd: null pointer");
+namespace dsg {
+int launch_attention_bwd_tc(const __half* qkv, const __half* o, const __half* dout, const float* lse, __half* dqkv, int n,
+                            int tokens, int heads, int head_dim, cudaStream_t st);  // attention_bwd_tc.cu
+}
+
+extern "C" int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws,
+                                 const float* lse, int32_t n, int32_t tokens, int32_t heads, int32_t head_dim,
+                                 void* stream) {
+  DSG_CHECK_ARG(qkv && out && dout && dqkv && (ws || lse), "dsg_attention_bwd: null pointer");
   DSG_CHECK_ARG(head_dim == AB_D, "dsg_attention_bwd: head_dim %d not supported (only 8)", head_dim);
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && tokens > 0 && heads > 0 && heads <= 65535, "dsg_attention_bwd: bad sizes");
   DSG_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)out | (uintptr_t)dout | (uintptr_t)dqkv) % 16) == 0,
                 "dsg_attention_bwd: unaligned pointer");
   if (n == 0) return DSG_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (lse) {  // tcgen05 path: needs the forward's log-sum-exp (dsg_attention_train)
+    const int rc = launch_attention_bwd_tc((const __half*)qkv, (const __half*)out, (const __half*)dout, lse,
+                                           (__half*)dqkv, n, tokens, heads, head_dim, st);
+    if (rc <= 0) return rc;
+    DSG_CHECK_ARG(ws != nullptr, "dsg_attention_bwd: shape outside the tcgen05 kernel and no workspace given");
+  }
   const float scale = 1.0f / sqrtf((float)head_dim);
   const float scale_log2 = scale * 1.4426950408889634f;
-  float* lse = ws;
+  float* lse_ws = ws;
   float* delta = ws + (int64_t)n * heads * tokens;
   const dim3 grid(ceil_div(tokens, AB_ROWS), heads, n);
-  attn_bwd_prep_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)out, (const __half*)dout, lse,
+  attn_bwd_prep_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)out, (const __half*)dout, lse_ws,
                                                  delta, tokens, heads, scale_log2);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention_bwd/prep");
-  attn_bwd_dkv_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)dout, lse, delta, (__half*)dqkv,
+  attn_bwd_dkv_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)dout, lse_ws, delta, (__half*)dqkv,
                                                 tokens, heads, scale, scale_log2);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention_bwd/dkv");
-  attn_bwd_dq_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)dout, lse, delta, (__half*)dqkv,
+  attn_bwd_dq_kernel<<<grid, AB_ROWS, 0, st>>>((const __half*)qkv, (const __half*)dout, lse_ws, delta, (__half*)dqkv,
                                                tokens, heads, scale, scale_log2);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention_bwd/dq");
   return DSG_OK;

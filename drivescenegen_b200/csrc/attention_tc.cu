@@ -57,7 +57,7 @@ __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128
 // dbg (optional, tests): float[128*128 + 128*16]: S of (first pair, tile 0, key block 0) and the raw O of that tile.
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n_pairs, int tokens, int heads,
-                    float scale_log2e, float* __restrict__ dbg) {
+                    float scale_log2e, float* __restrict__ dbg, float* __restrict__ lse_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* Ks = smem;                                 // tokens * 16
@@ -216,6 +216,8 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
 #pragma unroll
         for (int j = 0; j < 16; ++j) dbg[128 * 128 + row * 16 + j] = __uint_as_float(o[j]);
       }
+      // training: log2-sum-exp of the scaled scores of this row (the backward recomputes p = 2^(s c - lse))
+      if (lse_out) lse_out[(int64_t)pair * tokens + qt * 128 + row] = msc + log2f(__uint_as_float(o[8]));
       const float inv = 1.0f / __uint_as_float(o[8]);
       float f[8];
 #pragma unroll
@@ -246,7 +248,7 @@ static int atc_sms() {
 
 // returns DSG_OK, an error, or 1 when the shape is outside the kernel (head_dim != 8, tokens % 128, tokens > 4096)
 int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int heads, int head_dim, float* dbg,
-                        cudaStream_t st) {
+                        float* lse_out, cudaStream_t st) {
   if (head_dim != 8 || tokens % 128 != 0 || tokens > 4096 || tokens < 128) return 1;
   size_t sm = (size_t)tokens * 32 + 4096 + 256 + 2048 + 64 + 128;
   if (sm < 120 * 1024) sm = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
@@ -259,7 +261,7 @@ int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int h
   const int pairs = n * heads;
   const int grid = pairs < atc_sms() ? pairs : atc_sms();
   attention_tc_kernel<<<grid, ATC_THREADS, sm, st>>>(qkv, out, pairs, tokens, heads,
-                                                     1.4426950408889634f / sqrtf(8.0f), dbg);
+                                                     1.4426950408889634f / sqrtf(8.0f), dbg, lse_out);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention/tcgen05");
   return DSG_OK;
 }

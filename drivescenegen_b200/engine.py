@@ -468,12 +468,21 @@ class _Program:
         qkv = self._tmp("qkv", hw, 3 * ch)
         self._conv(3, act, hw, ch, 3 * ch, f"{pre}.qkv", f"{pre}.qkv.b", qkv)
         o = self._tmp("attn_o", hw, ch)
-        args = (qkv.data_ptr(), o.data_ptr(), b, hw[0] * hw[1], ch // hd, hd)
         ntok = hw[0] * hw[1]
-        self._emit("attention", {"flops": 4 * b * ntok * ntok * ch, "exps": b * (ch // hd) * ntok * ntok},
-                   lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
+        lse = self._attn_lse(b, ch // hd, ntok, hd)
+        meta = {"flops": 4 * b * ntok * ntok * ch, "exps": b * (ch // hd) * ntok * ntok}
+        if lse is not None:   # training forward: the tcgen05 kernel also leaves the log-sum-exp for the backward
+            args = (qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), b, ntok, ch // hd, hd)
+            self._emit("attention", meta, lambda st, a_=args: check(lib.dsg_attention_train(*a_, st), "attention"))
+        else:
+            args = (qkv.data_ptr(), o.data_ptr(), b, ntok, ch // hd, hd)
+            self._emit("attention", meta, lambda st, a_=args: check(lib.dsg_attention(*a_, st), "attention"))
         self._conv(3, o, hw, ch, ch, f"{pre}.out", f"{pre}.out.b", out, residual=x)
-        return {"kind": "attn", "a": a, "x": x, "hw": hw, "out": out, "act": act, "qkv": qkv, "o": o, "st1": st1}
+        return {"kind": "attn", "a": a, "x": x, "hw": hw, "out": out, "act": act, "qkv": qkv, "o": o, "st1": st1,
+                "lse": lse}
+
+    def _attn_lse(self, b: int, heads: int, tokens: int, hd: int) -> Optional[torch.Tensor]:
+        return None   # inference keeps no softmax statistics (the training program does)
 
     def _record(self, rec: dict):
         """hook: the training program keeps what each block produced (engine_train.py); inference drops it."""

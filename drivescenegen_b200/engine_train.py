@@ -53,6 +53,12 @@ class TrainProgram(_Program):
         self.te_saved = self.eng.arena.get(f"train/{self.b}/te_saved", self.b * (2 * half + 3 * hidden), torch.float32)
         return self.te_saved
 
+    def _attn_lse(self, b: int, heads: int, tokens: int, hd: int) -> Optional[torch.Tensor]:
+        if not self.lib.dsg_attention_train_tc_ok(tokens, hd):
+            return None
+        self._uid += 1
+        return self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/lse{self._uid}", b * heads * tokens, torch.float32)
+
     def _record(self, rec: dict):
         self.records.append(rec)
 
@@ -301,8 +307,8 @@ class TrainProgram(_Program):
         heads = ch // hd
         aws = self._btmp("attn_ws", 2 * b * heads * npx, torch.float32)
         if not self._sizing:
-            args = (rec["qkv"].data_ptr(), rec["o"].data_ptr(), do.data_ptr(), dqkv.data_ptr(), aws.data_ptr(), b, npx,
-                    heads, hd)
+            args = (rec["qkv"].data_ptr(), rec["o"].data_ptr(), do.data_ptr(), dqkv.data_ptr(), aws.data_ptr(),
+                    _p(rec["lse"]), b, npx, heads, hd)
             self._bemit("attention_bwd", {"flops": 10 * b * npx * npx * ch},
                         lambda st: check(lib.dsg_attention_bwd(*args, st), "attention_bwd"))
         # q/k/v projections: the fused [3c] gradient is scattered to the three parameter pairs

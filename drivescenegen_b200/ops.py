@@ -310,14 +310,27 @@ def small_wgrad(wide, narrow, conv_out_form: bool, inv_scale=None):
     return dw, nsum
 
 
-def attention_bwd(qkv, out, dout, heads: int, head_dim: int):
-    _cuda(qkv, out, dout)
+def attention_train(qkv, heads: int, head_dim: int):
+    """training forward on the tcgen05 kernel: returns (out fp16 [n,tokens,c], lse fp32 [n,heads,tokens])."""
+    _cuda(qkv)
+    lib = _lib.load()
+    n, tokens, c3 = qkv.shape
+    out = torch.empty((n, tokens, c3 // 3), dtype=torch.float16, device=qkv.device)
+    lse = torch.empty((n, heads, tokens), dtype=torch.float32, device=qkv.device)
+    check(lib.dsg_attention_train(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), n, tokens, heads, head_dim,
+                                  _st(qkv)), "attention_train")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, heads: int, head_dim: int, lse=None):
+    """lse given (attention_train): tcgen05 backward; else the CUDA-core kernels."""
+    _cuda(qkv, out, dout, lse)
     lib = _lib.load()
     n, tokens, _ = qkv.shape
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(2 * n * heads * tokens, dtype=torch.float32, device=qkv.device)
-    check(lib.dsg_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(), n,
-                                tokens, heads, head_dim, _st(qkv)), "attention_bwd")
+    check(lib.dsg_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), ws.data_ptr(),
+                                _p(lse), n, tokens, heads, head_dim, _st(qkv)), "attention_bwd")
     return dqkv
 
 

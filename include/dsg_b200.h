@@ -240,10 +240,19 @@ int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, i
                     int32_t nc, int32_t conv_out_form, float* partial, int32_t parts, const float* inv_scale, float* dw,
                     float* narrow_sum, void* stream);
 
-/* Backward of dsg_attention (head_dim 8 only): dqkv h16 [n][tokens][3*c] from qkv, the forward output `out` and its
- * gradient `dout` (both h16 [n][tokens][c]).  ws: float[2 * n * heads * tokens] scratch. */
-int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, int32_t n,
-                      int32_t tokens, int32_t heads, int32_t head_dim, void* stream);
+/* Training forward of the attention core on the tcgen05 kernel: like dsg_attention, and also writes
+ * lse float[n][heads][tokens], the log2-sum-exp of each query's scaled scores, for dsg_attention_bwd.
+ * Shapes: dsg_attention_train_tc_ok(tokens, head_dim) == 1 (head_dim 8, tokens a multiple of 128 in [128, 2048]). */
+int dsg_attention_train_tc_ok(int32_t tokens, int32_t head_dim);
+int dsg_attention_train(const void* qkv, void* out, float* lse, int32_t n, int32_t tokens, int32_t heads,
+                        int32_t head_dim, void* stream);
+/* Backward of the attention core (head_dim 8 only): dqkv h16 [n][tokens][3*c] from qkv, the forward output `out` and
+ * its gradient `dout` (both h16 [n][tokens][c]).
+ *   lse != NULL (from dsg_attention_train): tcgen05 kernel (two passes of recomputed probabilities, TMEM operands);
+ *   lse == NULL: CUDA-core flash-style kernels, any token count; ws: float[2 * n * heads * tokens] scratch
+ *   (ws may be NULL when lse is given and the shape is inside the tcgen05 kernel). */
+int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, const float* lse,
+                      int32_t n, int32_t tokens, int32_t heads, int32_t head_dim, void* stream);
 
 /* Global gradient norm over one flat fp32 buffer: out3 = { ||g|| * inv_loss_scale, coefficient that unscales and clips
  * (inv_loss_scale * min(1, max_norm / (norm + 1e-6)); max_norm <= 0 disables clipping), 1 if the norm is inf/nan }.

@@ -192,6 +192,17 @@ def test_attention_bwd_matches_autograd(shape):
     for i, nm in enumerate("qkv"):
         err = _rel(got[..., i * c:(i + 1) * c], ref[..., i * c:(i + 1) * c])
         assert err < 5e-3, f"d{nm}: rel {err}"
+    if tokens % 128 == 0:
+        # tcgen05 path: forward with log-sum-exp, backward from it (fp16 P / dS operands: ~1e-3 each)
+        o_tc, lse = ops.attention_train(qkv, heads, hd)
+        assert _rel(o_tc, o16) < 3e-3
+        s = torch.einsum("bhid,bhjd->bhij", q.detach(), k.detach()) / math.sqrt(hd)
+        lse_ref = torch.logsumexp(s, -1) / math.log(2.0)
+        assert (lse - lse_ref).abs().max().item() < 2e-3
+        got = ops.attention_bwd(qkv, o_tc, do, heads, hd, lse=lse)
+        for i, nm in enumerate("qkv"):
+            err = _rel(got[..., i * c:(i + 1) * c], ref[..., i * c:(i + 1) * c])
+            assert err < 1e-2, f"tcgen05 d{nm}: rel {err}"
 
 
 def test_conv_out_and_conv_in_backward():
