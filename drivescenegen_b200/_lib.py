@@ -56,6 +56,17 @@ class WgradArgs(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """mirror of ``dsg_pack_job`` (include/dsg_b200.h)."""
+    _fields_ = [
+        ("mode", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32), ("csc", C.c_int32),
+        ("w", C.c_void_p),
+        ("w_sc", C.c_void_p),
+        ("out", C.c_void_p),
+        ("k_total", C.c_int64), ("rows", C.c_int64), ("chunk_begin", C.c_int64),
+    ]
+
+
 _i32, _i64, _p, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/dsg_b200.h declares (tests check this)
@@ -80,6 +91,8 @@ SIGNATURES = {
     "dsg_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dsg_attention_ex": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     # ---- training path
+    "dsg_pack_job_chunks": (_i64, [_i64, _i64]),
+    "dsg_pack_conv_weights_batched": (C.c_int, [_p, _i32, _i64, _p]),
     "dsg_packed_k_dgrad": (_i64, [_i32, _i32]),
     "dsg_packed_rows_dgrad": (_i64, [_i32, _i32]),
     "dsg_grad_scale": (C.c_int, [_p, _i64, _p, _i32, _p, _p]),

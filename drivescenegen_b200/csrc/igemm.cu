@@ -254,12 +254,9 @@ __global__ void __launch_bounds__(256) igemm_naive_kernel(const __grid_constant_
 // modes 10-13: the data-gradient ("dgrad") forms of modes 0-3 — the same fp32 OIHW weight, packed so that the
 //           gradient w.r.t. the conv INPUT is itself a dsg_conv over the output gradient (cout/cin below are the
 //           FORWARD conv's): 10 -> run as mode 0, 11 -> run as mode 2, 12 -> run as mode 4, 13 -> run as mode 3
-__global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float* __restrict__ w, int cout, int cin,
-                                                          const float* __restrict__ wsc, int csc,
-                                                          __half* __restrict__ out, int64_t k_total, int64_t rows) {
-  const int64_t total = rows * k_total;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / k_total, k = i - r * k_total;
+// one packed element: row r, column k of the [rows][k_total] fp16 GEMM weight (modes above)
+__device__ __forceinline__ float pack_value(int mode, const float* __restrict__ w, int cout, int cin,
+                                            const float* __restrict__ wsc, int csc, int64_t r, int64_t k) {
     float v = 0.f;
     if (mode == 0 || mode == 1) {
       if (k < (int64_t)9 * cin) {
@@ -309,7 +306,41 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float*
     } else {  // mode 13: dgrad of mode 3 (transpose)
       v = w[k * cin + r];
     }
-    out[i] = __float2half_rn(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float* __restrict__ w, int cout, int cin,
+                                                          const float* __restrict__ wsc, int csc,
+                                                          __half* __restrict__ out, int64_t k_total, int64_t rows) {
+  const int64_t total = rows * k_total;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k_total, k = i - r * k_total;
+    out[i] = __float2half_rn(pack_value(mode, w, cout, cin, wsc, csc, r, k));
+  }
+}
+
+// Every conv weight of the model in ONE launch (a training step re-packs all of them after each optimizer step):
+// jobs[] lives in device memory; chunk c (PACK_CHUNK consecutive packed elements) belongs to the job with the largest
+// chunk_begin <= c.
+constexpr int PACK_CHUNK = 2048;
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dsg_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const int64_t c = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].chunk_begin <= c) lo = mid; else hi = mid - 1;
+  }
+  const dsg_pack_job j = jobs[lo];
+  const int64_t total = j.rows * j.k_total;
+  const int64_t base = (c - j.chunk_begin) * PACK_CHUNK;
+  __half* out = (__half*)j.out;
+#pragma unroll
+  for (int u = 0; u < PACK_CHUNK / 256; ++u) {
+    const int64_t i = base + u * 256 + threadIdx.x;
+    if (i < total) {
+      const int64_t r = i / j.k_total, k = i - r * j.k_total;
+      out[i] = __float2half_rn(pack_value(j.mode, j.w, j.cout, j.cin, j.w_sc, j.csc, r, k));
+    }
   }
 }
 
@@ -476,6 +507,16 @@ int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_
   pack_weight_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mode, w_oihw, cout, cin, w_sc, csc,
                                                                         (__half*)wpacked, k_total, rows);
   DSG_CUDA_LAUNCH_CHECK("dsg_pack_conv_weight");
+  return DSG_OK;
+}
+
+int64_t dsg_pack_job_chunks(int64_t rows, int64_t k_total) { return ceil_div64(rows * k_total, PACK_CHUNK); }
+
+int dsg_pack_conv_weights_batched(const dsg_pack_job* jobs_dev, int32_t njobs, int64_t total_chunks, void* stream) {
+  DSG_CHECK_ARG(jobs_dev && njobs >= 1 && total_chunks >= 1 && total_chunks < (int64_t)1 << 31,
+                "dsg_pack_conv_weights_batched: bad args");
+  pack_weights_batched_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+  DSG_CUDA_LAUNCH_CHECK("dsg_pack_conv_weights_batched");
   return DSG_OK;
 }
 

@@ -70,6 +70,9 @@ class UNetEngine:
         self.packed = False
         self.conv_impl = 0       # 0 = tcgen05 igemm, 1 = plain CUDA cross-check kernel (tests only)
         self.block_n_override = 0
+        self._stage: Dict[str, torch.Tensor] = {}
+        self._aliased = set()
+        self._jobs, self._job_keep, self._jobs_uploaded = [], [], None
         self.train_packs = False  # also pack the data-gradient forms of every conv weight (training path)
         self.train_programs: Dict[Tuple[int, int, int, int], object] = {}
         self._build_topology()
@@ -138,47 +141,89 @@ class UNetEngine:
         self.n_levels = len(boc)
 
     # ------------------------------------------------------------------ weights
+    def _src_f32(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """An fp32, contiguous, on-device source for a pack job with a STABLE address: the tensor itself when it
+        already is one (parameters of a model living on this device), else a persistent staging copy."""
+        t = t.detach()
+        if t.device == self.device and t.dtype == torch.float32 and t.is_contiguous():
+            return t
+        buf = self._stage.get(name)
+        if buf is None or buf.shape != t.shape:
+            buf = torch.empty(t.shape, dtype=torch.float32, device=self.device)
+            self._stage[name] = buf
+        buf.copy_(t)
+        return buf
+
     def _pack_conv(self, name: str, mode: int, w: torch.Tensor, w_sc: Optional[torch.Tensor] = None):
-        w = w.detach().to(self.device, torch.float32).contiguous()
+        """queue one weight-packing job (all jobs of a load_state_dict run as ONE launch, _run_pack_jobs)."""
+        w = self._src_f32(name + "/w", w)
         cout, cin = int(w.shape[0]), int(w.shape[1])
         csc = 0
         if w_sc is not None:
-            w_sc = w_sc.detach().to(self.device, torch.float32).reshape(cout, -1).contiguous()
+            w_sc = self._src_f32(name + "/wsc", w_sc.detach().reshape(cout, -1))
             csc = int(w_sc.shape[1])
         k = self.lib.dsg_packed_k(mode, cin, csc)
         rows = self.lib.dsg_packed_rows(mode, cout)
         out = self._weight_buf(name, rows * k, torch.float16)
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        check(self.lib.dsg_pack_conv_weight(mode, w.data_ptr(), cout, cin, _p(w_sc), csc, out.data_ptr(), st),
-              f"pack {name}")
-        self.weights[name] = out
+        self._jobs.append((mode, cout, cin, csc, w.data_ptr(), 0 if w_sc is None else w_sc.data_ptr(), out.data_ptr(),
+                           int(k), int(rows)))
+        self._job_keep.extend([w, w_sc])
 
     def _pack_dgrad(self, name: str, fwd_mode: int, w: torch.Tensor):
         """data-gradient packing of a conv weight (pack modes 10-13, include/dsg_b200.h)."""
-        w = w.detach().to(self.device, torch.float32).contiguous()
-        if w.dim() == 2:
-            w = w[:, :, None, None]
+        w = self._src_f32(name + "/w", w)
         cout, cin = int(w.shape[0]), int(w.shape[1])
         k = self.lib.dsg_packed_k_dgrad(fwd_mode, cout)
         rows = self.lib.dsg_packed_rows_dgrad(fwd_mode, cin)
         out = self._weight_buf(name, rows * k, torch.float16)
+        self._jobs.append((10 + fwd_mode, cout, cin, 0, w.data_ptr(), 0, out.data_ptr(), int(k), int(rows)))
+        self._job_keep.append(w)
+
+    def _run_pack_jobs(self):
+        """ONE kernel launch packs every conv weight (dsg_pack_conv_weights_batched); the device-side job table is
+        rebuilt only when a pointer or shape changed."""
+        if not self._jobs:
+            return
+        if self._jobs != self._jobs_uploaded:
+            arr = (_lib.PackJob * len(self._jobs))()
+            chunk = 0
+            for j, (mode, cout, cin, csc, w, wsc, out, k, rows) in zip(arr, self._jobs):
+                j.mode, j.cout, j.cin, j.csc = mode, cout, cin, csc
+                j.w, j.w_sc, j.out = w, (wsc or None), out
+                j.k_total, j.rows, j.chunk_begin = k, rows, chunk
+                chunk += int(self.lib.dsg_pack_job_chunks(rows, k))
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._jobs_dev = raw.to(self.device)
+            self._jobs_chunks = chunk
+            self._jobs_uploaded = list(self._jobs)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        check(self.lib.dsg_pack_conv_weight(10 + fwd_mode, w.data_ptr(), cout, cin, None, 0, out.data_ptr(), st),
-              f"pack dgrad {name}")
-        self.weights[name] = out
+        check(self.lib.dsg_pack_conv_weights_batched(self._jobs_dev.data_ptr(), len(self._jobs), self._jobs_chunks, st),
+              "pack weights (batched)")
 
     def _weight_buf(self, name: str, numel: int, dtype) -> torch.Tensor:
         """Packed-weight buffers keep their address across re-packs (a training step re-packs every step, and the
         execution programs hold raw pointers); a new or resized buffer invalidates the programs."""
         t = self.weights.get(name)
-        if t is None or t.numel() != numel or t.dtype != dtype:
+        if t is None or t.numel() != numel or t.dtype != dtype or name in self._aliased:
             t = torch.empty(numel, dtype=dtype, device=self.device)
             self.weights[name] = t
+            self._aliased.discard(name)
             self._new_weight_buffers = True
         return t
 
-    def _f32(self, name: str, t: torch.Tensor):
+    def _f32(self, name: str, t: torch.Tensor, alias: bool = True):
+        """fp32 side tensors (GroupNorm affines, biases, ...).  A parameter that already lives on this device as a
+        contiguous fp32 tensor is used IN PLACE (no copy; optimizers update it in place); anything else is copied into a
+        persistent buffer."""
         t = t.detach()
+        if alias and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and t.numel() > 0 \
+                and t.data_ptr() % 16 == 0:
+            old = self.weights.get(name)
+            if old is None or old.data_ptr() != t.data_ptr() or old.shape != t.shape:
+                self._new_weight_buffers = True
+            self.weights[name] = t
+            self._aliased.add(name)
+            return
         buf = self._weight_buf(name, t.numel(), torch.float32)
         if buf.shape != t.shape:
             buf = buf.view(t.shape)
@@ -188,27 +233,39 @@ class UNetEngine:
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         """(Re)pack all weights from a state dict with upstream key names."""
         self._new_weight_buffers = False
+        self._jobs, self._job_keep = [], []
         with torch.cuda.device(self.device):
             self._f32("conv_in.w", sd["conv_in.weight"])
             self._f32("conv_in.b", sd["conv_in.bias"])
             self._f32("conv_out.w", sd["conv_out.weight"])
             self._f32("conv_out.b", sd["conv_out.bias"])
             # tensor-core form of conv_out: output channels zero-padded to the smallest UMMA N (16)
-            wo = sd["conv_out.weight"].detach().to(self.device, torch.float32)
+            wo = sd["conv_out.weight"].detach()
             if wo.shape[0] <= 16 and wo.shape[1] % 64 == 0:
-                w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float32, device=self.device)
-                w16[: wo.shape[0]] = wo
-                b16 = torch.zeros(16, dtype=torch.float32, device=self.device)
-                b16[: wo.shape[0]] = sd["conv_out.bias"].detach().to(self.device, torch.float32)
+                w16 = self._stage.get("conv_out.w16")
+                if w16 is None or w16.shape[1:] != wo.shape[1:]:
+                    w16 = torch.zeros((16,) + tuple(wo.shape[1:]), dtype=torch.float32, device=self.device)
+                    self._stage["conv_out.w16"] = w16
+                    self._stage["conv_out.b16"] = torch.zeros(16, dtype=torch.float32, device=self.device)
+                b16 = self._stage["conv_out.b16"]
+                w16[: wo.shape[0]].copy_(wo)
+                b16[: wo.shape[0]].copy_(sd["conv_out.bias"].detach())
                 self._pack_conv("conv_out.w16", 0, w16)
-                self._f32("conv_out.b16", b16)
+                self.weights["conv_out.b16"] = b16
             self._f32("norm_out.g", sd["conv_norm_out.weight"])
             self._f32("norm_out.b", sd["conv_norm_out.bias"])
             for k in ("linear_1", "linear_2"):
                 self._f32(f"te.{k}.w", sd[f"time_embedding.{k}.weight"].t())   # [in][out]: see dsg_time_embed
                 self._f32(f"te.{k}.b", sd[f"time_embedding.{k}.bias"])
-            self._f32("te.proj.w", torch.cat([sd[r["prefix"] + ".time_emb_proj.weight"] for r in self.resnets], 0))
-            self._f32("te.proj.b", torch.cat([sd[r["prefix"] + ".time_emb_proj.bias"] for r in self.resnets], 0))
+            for nm, key in (("te.proj.w", ".time_emb_proj.weight"), ("te.proj.b", ".time_emb_proj.bias")):
+                parts = [sd[r["prefix"] + key].detach().to(self.device, torch.float32) for r in self.resnets]
+                shape = (sum(p.shape[0] for p in parts),) + tuple(parts[0].shape[1:])
+                buf = self._stage.get(nm)
+                if buf is None or buf.shape != shape:
+                    buf = torch.empty(shape, dtype=torch.float32, device=self.device)
+                    self._stage[nm] = buf
+                torch.cat(parts, 0, out=buf)
+                self._f32(nm, buf)
             half = self.time_dim // 2
             # exp table computed on the host exactly like upstream get_timestep_embedding (models/embeddings.py)
             exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32)
@@ -242,7 +299,7 @@ class UNetEngine:
                 b2 = sd[f"{pre}.conv2.bias"].detach().to(self.device, torch.float32)
                 if has_sc:
                     b2 = b2 + sd[f"{pre}.conv_shortcut.bias"].detach().to(self.device, torch.float32)
-                self._f32(f"{pre}.conv2.b", b2)
+                self._f32(f"{pre}.conv2.b", b2, alias=not has_sc)   # with a shortcut it is a derived sum: copy
                 r["has_sc"] = has_sc
                 if self.train_packs:
                     self._pack_dgrad(f"{pre}.conv1.dg", 0, sd[f"{pre}.conv1.weight"])
@@ -255,15 +312,21 @@ class UNetEngine:
                 pre = a["prefix"]
                 self._f32(f"{pre}.gn.g", sd[f"{pre}.group_norm.weight"])
                 self._f32(f"{pre}.gn.b", sd[f"{pre}.group_norm.bias"])
-                wqkv = torch.cat([sd[f"{pre}.to_q.weight"], sd[f"{pre}.to_k.weight"], sd[f"{pre}.to_v.weight"]], 0)
+                parts = [sd[f"{pre}.to_{n}.weight"].detach().to(self.device, torch.float32) for n in "qkv"]
+                wqkv = self._stage.get(f"{pre}.wqkv")
+                if wqkv is None:
+                    wqkv = torch.empty((3 * parts[0].shape[0], parts[0].shape[1], 1, 1), dtype=torch.float32,
+                                       device=self.device)
+                    self._stage[f"{pre}.wqkv"] = wqkv
+                torch.cat(parts, 0, out=wqkv.view(wqkv.shape[0], wqkv.shape[1]))
                 bqkv = torch.cat([sd[f"{pre}.to_q.bias"], sd[f"{pre}.to_k.bias"], sd[f"{pre}.to_v.bias"]], 0)
                 self._pack_conv(f"{pre}.qkv", 3, wqkv)
-                self._f32(f"{pre}.qkv.b", bqkv)
-                self._pack_conv(f"{pre}.out", 3, sd[f"{pre}.to_out.0.weight"])
+                self._f32(f"{pre}.qkv.b", bqkv, alias=False)
+                self._pack_conv(f"{pre}.out", 3, sd[f"{pre}.to_out.0.weight"].detach()[:, :, None, None])
                 self._f32(f"{pre}.out.b", sd[f"{pre}.to_out.0.bias"])
                 if self.train_packs:
                     self._pack_dgrad(f"{pre}.qkv.dg", 3, wqkv)
-                    self._pack_dgrad(f"{pre}.out.dg", 3, sd[f"{pre}.to_out.0.weight"])
+                    self._pack_dgrad(f"{pre}.out.dg", 3, sd[f"{pre}.to_out.0.weight"].detach()[:, :, None, None])
             for i, blk in enumerate(self.down):
                 if blk["down"]:
                     pre = f"down_blocks.{i}.downsamplers.0.conv"
@@ -278,9 +341,10 @@ class UNetEngine:
                     self._f32(pre + ".b", sd[pre + ".bias"])
                     if self.train_packs:
                         self._pack_dgrad(pre + ".dg", 2, sd[pre + ".weight"])
-        if self.train_packs:
-            for k in ("linear_1", "linear_2"):
-                self._f32(f"te.{k}.w_oi", sd[f"time_embedding.{k}.weight"])   # [out][in] for the backward
+            if self.train_packs:
+                for k in ("linear_1", "linear_2"):
+                    self._f32(f"te.{k}.w_oi", sd[f"time_embedding.{k}.weight"])   # [out][in] for the backward
+            self._run_pack_jobs()
         self.packed = True
         if self._new_weight_buffers:   # programs hold raw weight pointers
             self.programs.clear()
