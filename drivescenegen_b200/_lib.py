@@ -100,7 +100,7 @@ SIGNATURES = {
     "dsg_lin_dgrad_small": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "dsg_lin_wgrad_small": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dsg_gn_bwd": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _p,
-                             _i32, _i32, _i64, _i32, _p]),
+                             _p, _p, _i32, _i32, _i64, _i32, _p]),
     "dsg_gn_bwd_params": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dsg_colsum_h16": (C.c_int, [_p, _i64, _i32, _p, _i32, _p]),
     "dsg_colsum_finalize": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p]),

@@ -11,6 +11,7 @@
 // Replaces the cuDNN dgrad/wgrad autograd runs for UNet2DModel.conv_in / conv_out (diffusers 0.20.0 models/unet_2d.py)
 // from `accelerator.backward(loss)` (DriveSceneGen/pipeline/training_pipeline.py:86).
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace dsg {
 
@@ -36,9 +37,17 @@ __global__ void __launch_bounds__(SB_THREADS) amax_partial_kernel(const float* _
     partial[blockIdx.x] = m;
   }
 }
-__global__ void grad_scale_finalize_kernel(const float* __restrict__ partial, int parts, float* __restrict__ scale) {
+__global__ void __launch_bounds__(256) grad_scale_finalize_kernel(const float* __restrict__ partial, int parts,
+                                                                  float* __restrict__ scale) {
   float m = 0.f;
-  for (int i = 0; i < parts; ++i) m = fmaxf(m, partial[i]);
+  for (int i = threadIdx.x; i < parts; i += 256) m = fmaxf(m, partial[i]);   // max is order-independent
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i]);
   float s = 1.0f;
   if (m > 0.f && m <= 3.0e38f) {
     int e;
@@ -62,7 +71,9 @@ __global__ void __launch_bounds__(256) conv_out_dgrad_weight_kernel(const float*
   wt[i] = s * w[((int64_t)c * wc + ci) * 9 + (8 - t)];
 }
 
-// grid-stride over image rows; thread = (wide channel, x slice); 9 * NC accumulators per thread
+// grid-stride over image rows; thread = (PAIR of wide channels, x slice); 2 * 9 * NC accumulators per thread.
+// The pixel loop is unrolled four deep with the loads issued first: one 4-byte load per pixel per thread is pure
+// latency otherwise.
 template <int NC>
 __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* __restrict__ wide,
                                                                  const float* __restrict__ narrow, int n, int h, int w,
@@ -71,15 +82,19 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
   const int ws = w + 2;
   float* s_rows = sm;
   float* s_red = sm + NC * 3 * ws;  // [slices][NC * 9][wc] reused after the loop
-  const int c_t = threadIdx.x % wc, slice = threadIdx.x / wc, nslices = SB_THREADS / wc;
-  float acc[NC][9];
+  const int wc2 = wc >> 1;
+  const int c_t = threadIdx.x % wc2, slice = threadIdx.x / wc2, nslices = SB_THREADS / wc2;
+  float acc[NC][9][2];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
-  float csum = 0.f;  // thread c < NC: plain sum of narrow channel c (the conv_out bias gradient)
+    for (int t = 0; t < 9; ++t) { acc[c][t][0] = 0.f; acc[c][t][1] = 0.f; }
+  float csum[NC];    // per-thread share of the plain sums of the narrow channels (the conv_out bias gradient)
+#pragma unroll
+  for (int c = 0; c < NC; ++c) csum[c] = 0.f;
   const int64_t rows = (int64_t)n * h;
   const int64_t plane = (int64_t)h * w;
+  constexpr int U = 4;
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const int nn = (int)(r / h), y = (int)(r % h);
     __syncthreads();
@@ -89,16 +104,25 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
       float v = 0.f;
       if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = narrow[((int64_t)nn * NC + c) * plane + (int64_t)yy * w + xx];
       s_rows[i] = v;
+      if (ry == 1) {
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) csum[cc] += (c == cc) ? v : 0.f;
+      }
     }
     __syncthreads();
-    if ((int)threadIdx.x < NC) {
-      const float* rr = s_rows + ((int)threadIdx.x * 3 + 1) * ws + 1;
-      for (int xx = 0; xx < w; ++xx) csum += rr[xx];
-    }
-    if (slice < nslices) {
-      const __half* wp = wide + (((int64_t)nn * h + y) * w) * wc + c_t;
-      for (int xx = slice; xx < w; xx += nslices) {
-        const float a = __half2float(wp[(int64_t)xx * wc]);
+    const __half2* wp = reinterpret_cast<const __half2*>(wide + (((int64_t)nn * h + y) * w) * wc) + c_t;
+    for (int x0 = slice; x0 < w; x0 += nslices * U) {
+      __half2 av[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = x0 + u * nslices;
+        av[u] = xx < w ? wp[(int64_t)xx * wc2] : __floats2half2_rn(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = x0 + u * nslices;
+        if (xx >= w) continue;
+        const float2 a = __half22float2(av[u]);
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
@@ -107,18 +131,21 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
             for (int kx = 0; kx < 3; ++kx) {
               // narrow at q + sgn * (ky - 1, kx - 1); smem column index = x + 1
               const int ry = 1 + sgn * (ky - 1), cx = xx + 1 + sgn * (kx - 1);
-              acc[c][ky * 3 + kx] = fmaf(a, s_rows[(c * 3 + ry) * ws + cx], acc[c][ky * 3 + kx]);
+              const float nv = s_rows[(c * 3 + ry) * ws + cx];
+              acc[c][ky * 3 + kx][0] = fmaf(a.x, nv, acc[c][ky * 3 + kx][0]);
+              acc[c][ky * 3 + kx][1] = fmaf(a.y, nv, acc[c][ky * 3 + kx][1]);
             }
       }
     }
   }
   __syncthreads();
-  if (slice < nslices) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
+  for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) s_red[(slice * NC * 9 + c * 9 + t) * wc + c_t] = acc[c][t];
-  }
+    for (int t = 0; t < 9; ++t) {
+      s_red[(slice * NC * 9 + c * 9 + t) * wc + 2 * c_t] = acc[c][t][0];
+      s_red[(slice * NC * 9 + c * 9 + t) * wc + 2 * c_t + 1] = acc[c][t][1];
+    }
   __syncthreads();
   float* o = partial + (int64_t)blockIdx.x * (NC * 9 * wc + NC);
   for (int i = threadIdx.x; i < NC * 9 * wc; i += SB_THREADS) {
@@ -126,27 +153,36 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
     for (int s = 0; s < nslices; ++s) t += s_red[s * NC * 9 * wc + i];
     o[i] = t;
   }
-  if ((int)threadIdx.x < NC) o[NC * 9 * wc + threadIdx.x] = csum;
+  // plain sums: warp shuffle, then the 8 warps in a fixed order
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const float v = warp_sum(csum[c]);
+    if ((threadIdx.x & 31) == 0) s_red[c * 8 + (threadIdx.x >> 5)] = v;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NC) {
+    float t = 0.f;
+    for (int i = 0; i < SB_THREADS / 32; ++i) t += s_red[threadIdx.x * 8 + i];
+    o[NC * 9 * wc + threadIdx.x] = t;
+  }
 }
 
-// partial [parts][nc*9*wc + nc] -> dw (layout: wide_major ? [wc][nc][9] : [nc][wc][9]) and optional narrow-sum [nc]
-__global__ void __launch_bounds__(256) small_wgrad_finalize_kernel(const float* __restrict__ partial, int parts, int nc,
-                                                                   int wc, int wide_major,
-                                                                   const float* __restrict__ inv_scale,
-                                                                   float* __restrict__ dw, float* __restrict__ nsum) {
+// reduced [nc*9*wc + nc] (already scaled) -> dw (layout: wide_major ? [wc][nc][9] : [nc][wc][9]) and narrow-sum [nc]
+__global__ void __launch_bounds__(256) small_wgrad_remap_kernel(const float* __restrict__ red, int nc, int wc,
+                                                                int wide_major, float* __restrict__ dw,
+                                                                float* __restrict__ nsum) {
   const int stride = nc * 9 * wc + nc;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= stride) return;
-  float t = 0.f;
-  for (int p = 0; p < parts; ++p) t += partial[(int64_t)p * stride + i];
+  const float t = red[i];
   if (i >= nc * 9 * wc) {
     if (nsum) nsum[i - nc * 9 * wc] = t;
     return;
   }
-  const float s = inv_scale ? inv_scale[0] : 1.0f;
   const int c_t = i % wc, tap = (i / wc) % 9, c = i / (9 * wc);
   const int64_t o = wide_major ? ((int64_t)c_t * nc + c) * 9 + tap : ((int64_t)c * wc + c_t) * 9 + tap;
-  dw[o] = t * s;
+  dw[o] = t;
 }
 
 }  // namespace dsg
@@ -159,7 +195,7 @@ int dsg_grad_scale(const float* dout, int64_t numel, float* partial, int32_t par
   DSG_CHECK_ARG(dout && partial && scale && numel >= 0 && parts >= 1 && parts <= 4096, "dsg_grad_scale: bad args");
   amax_partial_kernel<<<parts, SB_THREADS, 0, (cudaStream_t)stream>>>(dout, numel, partial);
   DSG_CUDA_LAUNCH_CHECK("dsg_grad_scale/amax");
-  grad_scale_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(partial, parts, scale);
+  grad_scale_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, parts, scale);
   DSG_CUDA_LAUNCH_CHECK("dsg_grad_scale/finalize");
   return DSG_OK;
 }
@@ -176,11 +212,12 @@ int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, i
                     int32_t nc, int32_t conv_out_form, float* partial, int32_t parts, const float* inv_scale, float* dw,
                     float* narrow_sum, void* stream) {
   DSG_CHECK_ARG(wide_h16 && narrow_nchw && partial && dw, "dsg_small_wgrad: null pointer");
-  DSG_CHECK_ARG(nc >= 1 && nc <= 4 && wc >= 8 && wc <= SB_THREADS && SB_THREADS % wc == 0,
-                "dsg_small_wgrad: need 1 <= nc <= 4 and wc a divisor of 256");
+  DSG_CHECK_ARG(nc >= 1 && nc <= 4 && wc >= 16 && wc <= 2 * SB_THREADS && (2 * SB_THREADS) % wc == 0,
+                "dsg_small_wgrad: need 1 <= nc <= 4 and wc an even divisor of 512");
+  DSG_CHECK_ARG((uintptr_t)wide_h16 % 4 == 0, "dsg_small_wgrad: unaligned pointer");
   DSG_CHECK_ARG(n >= 0 && h > 0 && w > 0 && parts >= 1, "dsg_small_wgrad: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nslices = SB_THREADS / wc;
+  const int nslices = SB_THREADS / (wc / 2);
   const size_t sm = (size_t)(nc * 3 * (w + 2) + nslices * nc * 9 * wc) * sizeof(float);
   DSG_CHECK_ARG(sm <= 200 * 1024, "dsg_small_wgrad: row too wide for shared memory");
   const int sgn = conv_out_form ? -1 : 1;
@@ -199,9 +236,13 @@ int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, i
   }
 #undef DSG_SW_LAUNCH
   DSG_CUDA_LAUNCH_CHECK("dsg_small_wgrad");
-  small_wgrad_finalize_kernel<<<ceil_div(nc * 9 * wc + nc, 256), 256, 0, st>>>(partial, parts, nc, wc,
-                                                                              conv_out_form ? 0 : 1, inv_scale, dw,
-                                                                              narrow_sum);
+  // fixed-order sum over the CTAs' partials into the scratch row that follows them, then the layout change
+  const int stride = nc * 9 * wc + nc;
+  float* red = partial + (int64_t)parts * stride;
+  reduce_rows_kernel<1><<<ceil_div(stride, 32), 256, 0, st>>>(partial, 1, parts, stride, 0, stride, nullptr, 0, 0,
+                                                              inv_scale, red, nullptr, nullptr);
+  DSG_CUDA_LAUNCH_CHECK("dsg_small_wgrad/reduce");
+  small_wgrad_remap_kernel<<<ceil_div(stride, 256), 256, 0, st>>>(red, nc, wc, conv_out_form ? 0 : 1, dw, narrow_sum);
   DSG_CUDA_LAUNCH_CHECK("dsg_small_wgrad/finalize");
   return DSG_OK;
 }

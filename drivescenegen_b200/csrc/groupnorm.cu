@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int act,
                                                               __half* __restrict__ y, int64_t hw, int groups,
-                                                              int64_t px_per_cta) {
+                                                              int64_t px_per_cta, double inv_cnt_s, double inv_cnt_q) {
   const int C = c1 + c2, V = C >> 3, cpg = C / groups;
   const int ppi = GN_THREADS / V;
   const int n = blockIdx.y;
@@ -113,6 +113,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
       if (pp < p_end) raw[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
     }
   }
+  // the affine parameters do not depend on the statistics either
+  float gm8[8], bt8[8];
+  if (active) {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + ch0), g1 = *reinterpret_cast<const float4*>(gamma + ch0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + ch0), b1 = *reinterpret_cast<const float4*>(beta + ch0 + 4);
+    gm8[0] = g0.x; gm8[1] = g0.y; gm8[2] = g0.z; gm8[3] = g0.w; gm8[4] = g1.x; gm8[5] = g1.y; gm8[6] = g1.z; gm8[7] = g1.w;
+    bt8[0] = b0.x; bt8[1] = b0.y; bt8[2] = b0.z; bt8[3] = b0.w; bt8[4] = b1.x; bt8[5] = b1.y; bt8[6] = b1.z; bt8[7] = b1.w;
+  }
   // exact integer totals per group (only whole groups are ever summed: conv epilogues store channel PAIRS in the even
   // slot).  Every thread fetches whole channels in ONE round of loads and adds them with shared-memory integer
   // atomics — order-independent — instead of 32 threads walking their group's channels one dependent load at a time.
@@ -129,22 +137,23 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   }
   __syncthreads();
   if ((int)threadIdx.x < groups) {
+    // mean and variance from the exact integer totals in double (the subtraction cancels); the reciprocal square root
+    // itself in fp32 — FP64 sqrt / divide are long sequences on this part and sit on every CTA's critical path
     const int g = threadIdx.x;
-    const double inv_cnt = 1.0 / ((double)hw * (double)cpg);
-    const double mg = (double)(long long)s_t[g][0] * (1.0 / 16777216.0) * inv_cnt;
-    double vg = (double)(long long)s_t[g][1] * (1.0 / 1048576.0) * inv_cnt - mg * mg;
+    const double mg = (double)(long long)s_t[g][0] * inv_cnt_s;
+    double vg = (double)(long long)s_t[g][1] * inv_cnt_q - mg * mg;
     if (vg < 0.0) vg = 0.0;
     s_mean[g] = (float)mg;
-    s_rstd[g] = (float)(1.0 / sqrt(vg + (double)eps));
+    s_rstd[g] = rsqrtf((float)vg + eps);
   }
   __syncthreads();
   if (!active) return;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int ch = ch0 + j, g = ch / cpg;
-    a[j] = gamma[ch] * s_rstd[g];
-    b[j] = beta[ch] - s_mean[g] * a[j];
+    const int g = (ch0 + j) / cpg;
+    a[j] = gm8[j] * s_rstd[g];
+    b[j] = bt8[j] - s_mean[g] * a[j];
   }
   while (p < p_end) {
     const int64_t pn = p + (int64_t)ppi * GN_ILP;
@@ -212,6 +221,7 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
   DSG_CHECK_ARG(C <= GN_MAX_C, "dsg_gn_apply: C=%d too large (max %d)", C, GN_MAX_C);
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_apply: bad n/hw");
   DSG_CHECK_ARG(gamma && beta && y, "dsg_gn_apply: null pointer");
+  DSG_CHECK_ARG(((uintptr_t)gamma | (uintptr_t)beta) % 16 == 0, "dsg_gn_apply: gamma / beta must be 16-byte aligned");
   DSG_CHECK_ARG(((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)y) % 16 == 0 &&
                     ((uintptr_t)stats1 | (uintptr_t)stats2) % 16 == 0,
                 "dsg_gn_apply: unaligned pointer");
@@ -227,7 +237,8 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
   if (ctas > 65535) { px_per_cta = ceil_div64(hw, 65535); ctas = ceil_div64(hw, px_per_cta); }
   gn_apply_kernel<<<dim3((unsigned)ctas, n), GN_THREADS, 0, (cudaStream_t)stream>>>(
       (const __half*)x1, c1, (const long long*)stats1, (const __half*)x2, c2, (const long long*)stats2, gamma, beta,
-      eps, act, (__half*)y, hw, groups, px_per_cta);
+      eps, act, (__half*)y, hw, groups, px_per_cta, 1.0 / 16777216.0 / ((double)hw * (double)(C / groups)),
+      1.0 / 1048576.0 / ((double)hw * (double)(C / groups)));
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_apply");
   return DSG_OK;
 }

@@ -15,6 +15,7 @@
 // per-CTA column sums of what it wrote (the time-embedding / conv1-bias gradient of a ResnetBlock).
 // Forward statistics come from the same int64 per-channel totals the forward used (groupnorm.cu).
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace dsg {
 
@@ -34,9 +35,12 @@ struct GnBwdArgs {
   const __half* addend;  // optional [n][hw][C]
   __half* dx1; int acc1;
   __half* dx2; int acc2;
-  float* colsum;      // optional [n][ctas][C]
+  float* colsum;      // optional [n][ctas][C]: column sums of the GroupNorm term
+  float* osum1;       // optional [n][ctas][c1]: column sums of the FINAL value written to dx1
+  float* osum2;       // optional [n][ctas][c2]: same for dx2
   int64_t hw; int groups;
   int64_t px_per_block;
+  double inv_cnt_s, inv_cnt_q;   // 2^-24 / count and 2^-20 / count (count = hw * channels per group)
 };
 
 // mean / rstd per group from the exact integer totals (same arithmetic as gn_apply_kernel)
@@ -56,12 +60,12 @@ __device__ __forceinline__ void gn_moments(const GnBwdArgs& a, int n, float* s_m
   __syncthreads();
   if ((int)threadIdx.x < a.groups) {
     const int g = threadIdx.x;
-    const double inv_cnt = 1.0 / ((double)a.hw * (double)cpg);
-    const double mg = (double)(long long)s_t[g][0] * (1.0 / 16777216.0) * inv_cnt;
-    double vg = (double)(long long)s_t[g][1] * (1.0 / 1048576.0) * inv_cnt - mg * mg;
+    // identical arithmetic to gn_apply_kernel (the backward must see the forward's mean / rstd bit for bit)
+    const double mg = (double)(long long)s_t[g][0] * a.inv_cnt_s;
+    double vg = (double)(long long)s_t[g][1] * a.inv_cnt_q - mg * mg;
     if (vg < 0.0) vg = 0.0;
     s_mean[g] = (float)mg;
-    s_rstd[g] = (float)(1.0 / sqrt(vg + (double)a.eps));
+    s_rstd[g] = rsqrtf((float)vg + a.eps);
   }
   __syncthreads();
 }
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   if (p_end > a.hw) p_end = a.hw;
   constexpr int ILP = 2;
   int64_t p = p_begin + prow;
+  const bool want_osum = (from1 ? a.osum1 : a.osum2) != nullptr;
   gn_moments(a, n, s_mean, s_rstd, s_t);
   {
     const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
@@ -199,9 +204,9 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
     }
     __syncthreads();
   }
-  float cs_acc[8];
+  float cs_acc[8], os_acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) cs_acc[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { cs_acc[j] = 0.f; os_acc[j] = 0.f; }
   if (active) {
     float ga[8], yb[8], pc[8], qc[8];
 #pragma unroll
@@ -239,7 +244,14 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
             cs_acc[j] += d;
             r[j] = (d + fa[j]) + fo[j];
           }
-          stg_v4(dst + (base_px + pp) * cs + co, pack8(r));
+          const uint4 packed = pack8(r);
+          stg_v4(dst + (base_px + pp) * cs + co, packed);
+          if (want_osum) {   // sums of what was actually stored (fp16-rounded), like a reader of the tensor would see
+            float rr[8];
+            unpack8(packed, rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) os_acc[j] += rr[j];
+          }
         }
       }
     }
@@ -258,22 +270,22 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
       o[c] = t;
     }
   }
-}
-
-// d gamma / d beta: sum the per-sample (A_c, B_c) slots (slot `chunks` of every sample) in a fixed order, scale, store
-__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ partial, int n, int chunks, int C,
-                                                            const float* __restrict__ inv_scale,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float tA = 0.f, tB = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float2 v = reinterpret_cast<const float2*>(partial + ((int64_t)i * (chunks + 1) + chunks) * C * 2)[c];
-    tA += v.x; tB += v.y;
+  if (a.osum1 || a.osum2) {
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_part[1][prow * C + ch0 + j] = os_acc[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GB_THREADS) {
+      float* base = c < a.c1 ? a.osum1 : a.osum2;
+      if (!base) continue;
+      const int cw = c < a.c1 ? a.c1 : a.c2, cc = c < a.c1 ? c : c - a.c1;
+      float t = 0.f;
+      for (int r = 0; r < ppi; ++r) t += s_part[1][r * C + c];
+      base[((int64_t)n * gridDim.x + blockIdx.x) * cw + cc] = t;
+    }
   }
-  const float s = inv_scale ? *inv_scale : 1.0f;
-  dbeta[c] = tA * s;
-  dgamma[c] = tB * s;
 }
 
 // column sums of an fp16 [rows][C] tensor: per-block partials [blocks][C] (fp32), fixed order inside a block
@@ -310,25 +322,6 @@ __global__ void __launch_bounds__(GB_THREADS) colsum_h16_kernel(const __half* __
   }
 }
 
-// partial [n][parts][C] -> per_n [n][per_n_stride] (+ per_n_off, raw) and total[c] = scale * sum over n and parts
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int n, int parts,
-                                                              int C, float* __restrict__ per_n, int per_n_stride,
-                                                              int per_n_off, const float* __restrict__ inv_scale,
-                                                              float* __restrict__ total, float* __restrict__ total2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float tot = 0.f;
-  for (int i = 0; i < n; ++i) {
-    float t = 0.f;
-    for (int k = 0; k < parts; ++k) t += partial[((int64_t)i * parts + k) * C + c];
-    if (per_n) per_n[(int64_t)i * per_n_stride + per_n_off + c] = t;
-    tot += t;
-  }
-  const float s = inv_scale ? *inv_scale : 1.0f;
-  if (total) total[c] = tot * s;
-  if (total2) total2[c] = tot * s;
-}
-
 }  // namespace dsg
 
 using namespace dsg;
@@ -338,7 +331,7 @@ extern "C" {
 int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
-               int32_t colsum_parts, int32_t n, int64_t hw, int32_t groups, void* stream) {
+               float* osum1, float* osum2, int32_t parts, int32_t n, int64_t hw, int32_t groups, void* stream) {
   DSG_CHECK_ARG(dy && x1 && stats1 && dx1 && c1 > 0 && c1 % 8 == 0, "dsg_gn_bwd: dy/x1/stats1/dx1 null or bad c1");
   DSG_CHECK_ARG((x2 == nullptr) == (c2 == 0) && (x2 == nullptr) == (stats2 == nullptr) &&
                     (x2 == nullptr) == (dx2 == nullptr) && c2 % 8 == 0,
@@ -348,8 +341,9 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
                 "dsg_gn_bwd: bad groups %d for C=%d", groups, C);
   DSG_CHECK_ARG(gamma && beta && partial && chunks >= 1 && chunks <= GB_MAX_CHUNKS, "dsg_gn_bwd: bad partial/chunks");
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_bwd: bad n/hw");
-  DSG_CHECK_ARG((colsum == nullptr) == (colsum_parts == 0) && colsum_parts >= 0 && colsum_parts <= 65535,
-                "dsg_gn_bwd: colsum/colsum_parts mismatch");
+  DSG_CHECK_ARG(parts >= 0 && parts <= 65535 && (parts > 0 || (!colsum && !osum1 && !osum2)),
+                "dsg_gn_bwd: column sums need an explicit parts > 0");
+  DSG_CHECK_ARG(osum2 == nullptr || x2 != nullptr, "dsg_gn_bwd: osum2 without x2");
   DSG_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)dx1 | (uintptr_t)dx2 |
                   (uintptr_t)addend | (uintptr_t)stats1 | (uintptr_t)stats2) % 16) == 0 && (uintptr_t)partial % 8 == 0,
                 "dsg_gn_bwd: unaligned pointer");
@@ -362,12 +356,14 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   a.partial = partial; a.chunks = chunks;
   a.addend = (const __half*)addend;
   a.dx1 = (__half*)dx1; a.acc1 = acc1; a.dx2 = (__half*)dx2; a.acc2 = acc2;
-  a.colsum = colsum; a.hw = hw; a.groups = groups;
+  a.colsum = colsum; a.osum1 = osum1; a.osum2 = osum2; a.hw = hw; a.groups = groups;
+  a.inv_cnt_s = 1.0 / 16777216.0 / ((double)hw * (double)(C / groups));
+  a.inv_cnt_q = 1.0 / 1048576.0 / ((double)hw * (double)(C / groups));
   cudaStream_t st = (cudaStream_t)stream;
   a.px_per_block = ceil_div64(hw, chunks);
   gn_bwd_stats_kernel<<<dim3((unsigned)chunks, n), GB_THREADS, 0, st>>>(a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
-  int64_t ctas = colsum_parts;
+  int64_t ctas = parts;
   if (ctas == 0) {
     ctas = (148 * 4) / n;
     if (ctas < 1) ctas = 1;
@@ -383,8 +379,10 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
 int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c, const float* inv_scale,
                       float* dgamma, float* dbeta, void* stream) {
   DSG_CHECK_ARG(partial && dgamma && dbeta && n >= 0 && chunks >= 1 && c > 0, "dsg_gn_bwd_params: bad args");
-  gn_bwd_params_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, n, chunks, c, inv_scale, dgamma,
-                                                                          dbeta);
+  // per-sample slot `chunks` of every sample holds (sum g, sum g * xh) per channel: d beta, d gamma
+  reduce_rows_kernel<2><<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(
+      partial + (int64_t)chunks * c * 2, n, 1, c, (int64_t)(chunks + 1) * c * 2, 0, nullptr, 0, 0, inv_scale, dbeta,
+      nullptr, dgamma);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd_params");
   return DSG_OK;
 }
@@ -402,9 +400,8 @@ int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32
 int dsg_colsum_finalize(const float* partial, int32_t n, int32_t parts, int32_t c, float* per_n, int32_t per_n_stride,
                         int32_t per_n_off, const float* inv_scale, float* total, float* total2, void* stream) {
   DSG_CHECK_ARG(partial && n >= 0 && parts >= 1 && c > 0, "dsg_colsum_finalize: bad args");
-  colsum_finalize_kernel<<<ceil_div(c, 256), 256, 0, (cudaStream_t)stream>>>(partial, n, parts, c, per_n,
-                                                                            per_n_stride, per_n_off, inv_scale, total,
-                                                                            total2);
+  reduce_rows_kernel<1><<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(
+      partial, n, parts, c, (int64_t)parts * c, c, per_n, per_n_stride, per_n_off, inv_scale, total, total2, nullptr);
   DSG_CUDA_LAUNCH_CHECK("dsg_colsum_finalize");
   return DSG_OK;
 }

@@ -81,10 +81,21 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 // out[0] = total L2 norm of (g * inv_loss_scale); out[1] = clip coefficient min(1, max_norm / (norm + 1e-6)) folded with
 // inv_loss_scale (multiply RAW gradients by out[1]); out[2] = 1 if the norm is not finite (skip the step), else 0
-__global__ void grad_norm_finalize_kernel(const double* __restrict__ partial, int parts, float inv_loss_scale,
-                                          float max_norm, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) grad_norm_finalize_kernel(const double* __restrict__ partial, int parts,
+                                                                 float inv_loss_scale, float max_norm,
+                                                                 float* __restrict__ out) {
+  // fixed assignment of partials to threads + fixed-order tree: deterministic, and not a chain of dependent loads
+  __shared__ double sm[256];
   double t = 0.0;
-  for (int i = 0; i < parts; ++i) t += partial[i];
+  for (int i = threadIdx.x; i < parts; i += 256) t += partial[i];
+  sm[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  t = sm[0];
   const float norm = (float)sqrt(t) * inv_loss_scale;
   const bool finite = norm <= 3.0e38f;  // false for inf and nan
   float coef = inv_loss_scale;
@@ -171,7 +182,7 @@ int dsg_grad_norm(const float* g, int64_t numel, double* partial, int32_t parts,
   DSG_CHECK_ARG(g && partial && out3 && numel >= 0 && parts >= 1 && parts <= 65535, "dsg_grad_norm: bad args");
   sumsq_partial_kernel<<<parts, 256, 0, (cudaStream_t)stream>>>(g, numel, partial);
   DSG_CUDA_LAUNCH_CHECK("dsg_grad_norm/partial");
-  grad_norm_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(partial, parts, inv_loss_scale, max_norm, out3);
+  grad_norm_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partial, parts, inv_loss_scale, max_norm, out3);
   DSG_CUDA_LAUNCH_CHECK("dsg_grad_norm/finalize");
   return DSG_OK;
 }

@@ -80,7 +80,9 @@ class TrainProgram(_Program):
         # pass 1 sizes the shared scratch buffers, pass 2 emits the ops (same trick as the forward)
         self._bwd_sizes: Dict[Tuple[str, torch.dtype], int] = {}
         self._sizing = True
+        self._gtotal: Dict[int, int] = {}
         self._emit_backward()
+        self._gtotal = dict(self._gcount)   # writers per gradient tensor
         for (key, dtype), numel in self._bwd_sizes.items():
             self.eng.arena.get(key, numel, dtype)
         self._sizing = False
@@ -96,9 +98,19 @@ class TrainProgram(_Program):
             g = self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/grad{len(self._gbuf)}", t.numel(), torch.float16)
             self._gbuf[key] = g
             self._gwritten[key] = False
+            self._gcount[key] = 0
         w = self._gwritten[key]
         self._gwritten[key] = True
+        self._gcount[key] += 1
         return g, w
+
+    def _is_last_writer(self, t: Optional[torch.Tensor]) -> bool:
+        """call right after _grad_buf(t): True when this is the final write to t's gradient (the writer counts come
+        from the sizing pass), i.e. the values stored now are the complete gradient."""
+        if t is None or self._sizing:
+            return False
+        key = t.data_ptr()
+        return self._gcount[key] == self._gtotal.get(key, -1)
 
     def _grad_ready(self, t: torch.Tensor) -> torch.Tensor:
         key = t.data_ptr()
@@ -120,6 +132,17 @@ class TrainProgram(_Program):
             check(lib.dsg_colsum_h16(*a1, st), "colsum_h16")
             check(lib.dsg_colsum_finalize(*a2, st), "colsum_finalize")
         self._bemit("colsum", {"bytes": rows * c * 2}, run)
+
+    def _bias_grad(self, t: torch.Tensor, g: torch.Tensor, rows: int, c: int, total, total2=None):
+        """bias gradient of the block that produced activation t = column sums of t's complete gradient g: taken from
+        the last writer's per-CTA sums when that was a GroupNorm backward, else one more read of g."""
+        rec = None if self._sizing else self._osum.get(t.data_ptr())
+        if rec is None:
+            return self._colsum_to(g, rows, c, total, total2)
+        buf, parts = rec
+        lib = self.lib
+        a = (buf.data_ptr(), self.b, parts, c, None, 0, 0, self.inv_scale_ptr, _p(total), _p(total2))
+        self._bemit("colsum_finalize", {}, lambda st: check(lib.dsg_colsum_finalize(*a, st), "colsum_finalize"))
 
     def _wgrad(self, mode, x, dy, hw, cin, cout, grad, ci_total=None, ci_off=0):
         lib = self.lib
@@ -158,20 +181,28 @@ class TrainProgram(_Program):
                     lambda st, r=ref: check(lib.dsg_conv(r, st), f"dgrad {wname}"))
 
     def _gn_bwd(self, dy, x1, c1, st1, x2, c2, st2, gname, bname, act, hw, addend, dx1, acc1, dx2, acc2,
-                g_gamma, g_beta, colsum_to=None):
-        """colsum_to = (per_n tensor, stride, offset, total tensor) or None."""
+                g_gamma, g_beta, colsum_to=None, last1=False, last2=False):
+        """colsum_to = (per_n tensor, stride, offset, total tensor) or None.  last1 / last2: this call completes the
+        gradient of x1 / x2 — it then also leaves that tensor's column sums (its producer's bias gradient)."""
         eng, lib, b = self.eng, self.lib, self.b
         c, npx = c1 + c2, hw[0] * hw[1]
         chunks = max(1, min(64, (148 * 4) // b, -(-npx // 64)))
         partial = self._btmp("gn_partial", b * (chunks + 1) * c * 2, torch.float32)
-        parts = max(1, min((148 * 4) // b, -(-npx // 32))) if colsum_to else 0
+        parts = max(1, min((148 * 4) // b, -(-npx // 32))) if (colsum_to or last1 or last2) else 0
         colsum = self._btmp("gn_colsum", max(1, b * parts * c), torch.float32) if colsum_to else None
         if self._sizing:
             return
+        osum = [None, None]
+        for i, (last, xs, cw) in enumerate(((last1, x1, c1), (last2, x2, c2))):
+            if last:
+                buf = eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/osum{len(self._osum)}", b * parts * cw,
+                                    torch.float32)
+                self._osum[xs.data_ptr()] = (buf, parts)
+                osum[i] = buf
         g, bt = eng.weights[gname], eng.weights[bname]
         a1 = (dy.data_ptr(), x1.data_ptr(), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps,
               act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1), _p(dx2), int(acc2), _p(colsum),
-              parts, b, npx, eng.groups)
+              _p(osum[0]), _p(osum[1]), parts, b, npx, eng.groups)
         a2 = (partial.data_ptr(), b, chunks, c, self.inv_scale_ptr, g_gamma.data_ptr(), g_beta.data_ptr())
         a3 = None
         if colsum_to:
@@ -192,6 +223,8 @@ class TrainProgram(_Program):
         G = self.grads
         self._gbuf: Dict[int, torch.Tensor] = {}
         self._gwritten: Dict[int, bool] = {}
+        self._gcount: Dict[int, int] = {}
+        self._osum: Dict[int, Tuple[torch.Tensor, int]] = {}   # tensor -> per-CTA column sums of its final gradient
         self.scale = eng.arena.get(f"train/{b}/scale", 2, torch.float32)
         self.scale_ptr = self.scale.data_ptr()
         self.inv_scale_ptr = self.scale.data_ptr() + 4
@@ -213,8 +246,9 @@ class TrainProgram(_Program):
         zero_b = self._btmp("zero_bias", c0, torch.float32)
         dact = self._btmp("dact", b * npx * c0)
         sw_parts = min(b * hw[0], 148 * 4)
-        sw_partial = self._btmp("small_wgrad_partial", sw_parts * (self.cout * 9 * c0 + self.cout), torch.float32)
+        sw_partial = self._btmp("small_wgrad_partial", (sw_parts + 1) * (self.cout * 9 * c0 + self.cout), torch.float32)
         gx, acc = self._grad_buf(x)
+        last = self._is_last_writer(x)
         if not self._sizing:
             zero_b.zero_()
             w_out = W["conv_out.w"]
@@ -232,7 +266,7 @@ class TrainProgram(_Program):
                                           G["conv_out.bias"].data_ptr(), st), "conv_out wgrad")
             self._bemit("conv_out_bwd", {"bytes": b * npx * (self.cout * 4 * 2 + c0 * 2 * 2)}, run)
         self._gn_bwd(dact, x, c0, rec["st1"], None, 0, None, "norm_out.g", "norm_out.b", 1, hw, None, gx, acc, None, 0,
-                     G["conv_norm_out.weight"], G["conv_norm_out.bias"])
+                     G["conv_norm_out.weight"], G["conv_norm_out.bias"], last1=last)
 
     def _bwd_in(self, rec):
         """conv_in: weight / bias gradient only (the input image needs no gradient)."""
@@ -240,9 +274,9 @@ class TrainProgram(_Program):
         G = self.grads
         out, hw, c0 = rec["out"], rec["hw"], rec["c0"]
         g = self._grad_ready(out)
-        self._colsum_to(g, b * hw[0] * hw[1], c0, G["conv_in.bias"])
+        self._bias_grad(out, g, b * hw[0] * hw[1], c0, G["conv_in.bias"])
         sw_parts = min(b * hw[0], 148 * 4)
-        sw_partial = self._btmp("small_wgrad_partial", sw_parts * (self.cin * 9 * c0 + self.cin), torch.float32)
+        sw_partial = self._btmp("small_wgrad_partial", (sw_parts + 1) * (self.cin * 9 * c0 + self.cin), torch.float32)
         if self._sizing:
             return
 
@@ -260,7 +294,7 @@ class TrainProgram(_Program):
         c, npx = c1 + c2, hw[0] * hw[1]
         g_out = self._grad_ready(out)
         # conv2 (+ shortcut): bias, weights
-        self._colsum_to(g_out, b * npx, co, G[f"{pre}.conv2.bias"],
+        self._bias_grad(out, g_out, b * npx, co, G[f"{pre}.conv2.bias"],
                         G[f"{pre}.conv_shortcut.bias"] if r["has_sc"] else None)
         self._wgrad(0, rec["a2"], g_out, hw, co, co, G[f"{pre}.conv2.weight"])
         if r["has_sc"]:
@@ -286,9 +320,11 @@ class TrainProgram(_Program):
             assert x2 is None and c1 == co
             addend = g_out
         gx1, acc1 = self._grad_buf(x1)
+        last1 = self._is_last_writer(x1)
         gx2, acc2 = self._grad_buf(x2) if x2 is not None else (None, False)
+        last2 = self._is_last_writer(x2)
         self._gn_bwd(dact, x1, c1, rec["st1"], x2, c2, rec["st2"], f"{pre}.norm1.g", f"{pre}.norm1.b", 1, hw, addend,
-                     gx1, acc1, gx2, acc2, G[f"{pre}.norm1.weight"], G[f"{pre}.norm1.bias"])
+                     gx1, acc1, gx2, acc2, G[f"{pre}.norm1.weight"], G[f"{pre}.norm1.bias"], last1=last1, last2=last2)
 
     def _bwd_attn(self, rec):
         eng, lib, b = self.eng, self.lib, self.b
@@ -298,7 +334,7 @@ class TrainProgram(_Program):
         npx = hw[0] * hw[1]
         g_out = self._grad_ready(out)
         # to_out: bias, weight, data gradient
-        self._colsum_to(g_out, b * npx, ch, G[f"{pre}.to_out.0.bias"])
+        self._bias_grad(out, g_out, b * npx, ch, G[f"{pre}.to_out.0.bias"])
         self._wgrad(3, rec["o"], g_out, hw, ch, ch, G[f"{pre}.to_out.0.weight"])
         do = self._btmp("attn_do", b * npx * ch)
         self._dgrad(3, g_out, hw, ch, ch, f"{pre}.out.dg", do, flops_k=2 * b * npx * ch * ch)
@@ -327,8 +363,9 @@ class TrainProgram(_Program):
         da = self._btmp("dact", b * npx * ch)
         self._dgrad(3, dqkv, hw, 3 * ch, ch, f"{pre}.qkv.dg", da, flops_k=2 * b * npx * 3 * ch * ch)
         gx, acc = self._grad_buf(x)
+        last = self._is_last_writer(x)
         self._gn_bwd(da, x, ch, rec["st1"], None, 0, None, f"{pre}.gn.g", f"{pre}.gn.b", 0, hw, g_out, gx, acc, None, 0,
-                     G[f"{pre}.group_norm.weight"], G[f"{pre}.group_norm.bias"])
+                     G[f"{pre}.group_norm.weight"], G[f"{pre}.group_norm.bias"], last1=last)
 
     def _bwd_down(self, rec):
         """Downsample2D conv (3x3 stride 2)."""
@@ -337,7 +374,7 @@ class TrainProgram(_Program):
         pre, x, hw, out, ch = rec["prefix"], rec["x"], rec["hw"], rec["out"], rec["ch"]
         ohw = (hw[0] // 2, hw[1] // 2)
         g_out = self._grad_ready(out)
-        self._colsum_to(g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
+        self._bias_grad(out, g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
         self._wgrad(1, x, g_out, hw, ch, ch, G[pre + ".weight"])
         gx, acc = self._grad_buf(x)
         # transpose of the stride-2 conv = a four-phase sub-pixel conv over the low-resolution gradient
@@ -351,7 +388,7 @@ class TrainProgram(_Program):
         pre, x, hw, out, ch = rec["prefix"], rec["x"], rec["hw"], rec["out"], rec["ch"]
         ohw = (hw[0] * 2, hw[1] * 2)
         g_out = self._grad_ready(out)
-        self._colsum_to(g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
+        self._bias_grad(out, g_out, b * ohw[0] * ohw[1], ch, G[pre + ".bias"])
         self._wgrad(2, x, g_out, hw, ch, ch, G[pre + ".weight"])
         gx, acc = self._grad_buf(x)
         self._dgrad(4, g_out, ohw, ch, ch, pre + ".dg", gx, residual=gx if acc else None,

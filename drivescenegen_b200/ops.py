@@ -210,8 +210,9 @@ def grad_scale(dout):
 
 
 def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=None, stats2=None, addend=None,
-           dx1=None, dx2=None, acc1=False, acc2=False, want_colsum=False, inv_scale=None):
-    """GroupNorm(+SiLU) backward.  Returns (dx1, dx2, dgamma, dbeta, colsum_per_sample or None)."""
+           dx1=None, dx2=None, acc1=False, acc2=False, want_colsum=False, inv_scale=None, want_osum=False):
+    """GroupNorm(+SiLU) backward.  Returns (dx1, dx2, dgamma, dbeta, colsum_per_sample or None) and, with want_osum,
+    additionally (column sums of the stored dx1 [c1], of the stored dx2 [c2] or None)."""
     _cuda(dy, x1, x2, gamma, beta, addend)
     lib = _lib.load()
     n, h, w, c1 = x1.shape
@@ -227,11 +228,13 @@ def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
         dx1 = torch.empty_like(x1)
     if x2 is not None and dx2 is None:
         dx2 = torch.empty_like(x2)
-    parts = max(1, min((148 * 4) // n, -(-hw // 32))) if want_colsum else 0
+    parts = max(1, min((148 * 4) // n, -(-hw // 32))) if (want_colsum or want_osum) else 0
     colsum = torch.empty((n, parts, c), dtype=torch.float32, device=dy.device) if want_colsum else None
+    osum1 = torch.empty((n, parts, c1), dtype=torch.float32, device=dy.device) if want_osum else None
+    osum2 = torch.empty((n, parts, c2), dtype=torch.float32, device=dy.device) if (want_osum and c2) else None
     check(lib.dsg_gn_bwd(dy.data_ptr(), x1.data_ptr(), c1, stats1.data_ptr(), _p(x2), c2, _p(stats2), gamma.data_ptr(),
                          beta.data_ptr(), eps, act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1),
-                         _p(dx2), int(acc2), _p(colsum), parts, n, hw, groups, _st(dy)), "gn_bwd")
+                         _p(dx2), int(acc2), _p(colsum), _p(osum1), _p(osum2), parts, n, hw, groups, _st(dy)), "gn_bwd")
     dgamma = torch.empty(c, dtype=torch.float32, device=dy.device)
     dbeta = torch.empty(c, dtype=torch.float32, device=dy.device)
     check(lib.dsg_gn_bwd_params(partial.data_ptr(), n, chunks, c, _p(inv_scale), dgamma.data_ptr(), dbeta.data_ptr(),
@@ -241,6 +244,17 @@ def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
         per_n = torch.empty((n, c), dtype=torch.float32, device=dy.device)
         check(lib.dsg_colsum_finalize(colsum.data_ptr(), n, parts, c, per_n.data_ptr(), c, 0, None, None, None,
                                       _st(dy)), "colsum_finalize")
+    if want_osum:
+        outs = []
+        for os_, cw in ((osum1, c1), (osum2, c2)):
+            if os_ is None:
+                outs.append(None)
+                continue
+            tot = torch.empty(cw, dtype=torch.float32, device=dy.device)
+            check(lib.dsg_colsum_finalize(os_.data_ptr(), n, parts, cw, None, 0, 0, None, tot.data_ptr(), None,
+                                          _st(dy)), "colsum_finalize")
+            outs.append(tot)
+        return dx1, dx2, dgamma, dbeta, per_n, outs[0], outs[1]
     return dx1, dx2, dgamma, dbeta, per_n
 
 
@@ -301,7 +315,7 @@ def small_wgrad(wide, narrow, conv_out_form: bool, inv_scale=None):
     n, h, w, wc = wide.shape
     nc = narrow.shape[1]
     parts = min(n * h, 148 * 4)
-    partial = torch.empty((parts, nc * 9 * wc + nc), dtype=torch.float32, device=wide.device)
+    partial = torch.empty((parts + 1, nc * 9 * wc + nc), dtype=torch.float32, device=wide.device)
     dw = torch.empty((nc, wc, 3, 3) if conv_out_form else (wc, nc, 3, 3), dtype=torch.float32, device=wide.device)
     nsum = torch.empty(nc, dtype=torch.float32, device=wide.device)
     check(lib.dsg_small_wgrad(wide.data_ptr(), narrow.data_ptr(), n, h, w, wc, nc, int(conv_out_form),

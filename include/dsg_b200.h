@@ -200,13 +200,16 @@ int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
  *   1 <= chunks <= 64.
  *   addend (may be NULL): h16 [n][hw][c1+c2] added to the input gradient (the ResnetBlock shortcut's gradient).
  *   dx1 / dx2: h16 gradients of x1 / x2; accN != 0 adds to the existing content (tensor with two consumers).
- *   colsum (may be NULL, then colsum_parts = 0): float[n][colsum_parts][c1+c2] receives per-CTA column sums of the
- *   GroupNorm term of dx (before addend / accumulate) — the time-embedding / conv bias gradient of a ResnetBlock;
- *   colsum_parts is also the number of CTAs per sample of the apply pass. */
+ *   parts: CTAs per sample of the apply pass (0 = automatic, only without column sums).  Optional per-CTA column sums
+ *   (finish them with dsg_colsum_finalize):
+ *     colsum float[n][parts][c1+c2]: of the GroupNorm term of dx (before addend / accumulate) — the time-embedding /
+ *            conv1-bias gradient of a ResnetBlock;
+ *     osum1 float[n][parts][c1], osum2 float[n][parts][c2]: of the FINAL values stored to dx1 / dx2 — when this call is
+ *            the last writer of that gradient tensor, its producer's bias gradient without another read. */
 int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
-               int32_t colsum_parts, int32_t n, int64_t hw, int32_t groups, void* stream);
+               float* osum1, float* osum2, int32_t parts, int32_t n, int64_t hw, int32_t groups, void* stream);
 /* d gamma[c] / d beta[c] = inv_scale * sum over samples of the per-sample slot dsg_gn_bwd left in `partial` */
 int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c, const float* inv_scale,
                       float* dgamma, float* dbeta, void* stream);
@@ -246,8 +249,8 @@ int dsg_conv_out_dgrad_weight(const float* w, int32_t cout, int32_t cin, const f
 /* Weight gradient of conv_in / conv_out: wide = the h16 [n][h][w][wc] side, narrow = the fp32 NCHW [n][nc][h][w] side.
  *   conv_out_form = 0 (conv_in):  dw fp32 [wc][nc][3][3] = inv_scale * sum wide[q][wc] * narrow[c][q + tap]
  *   conv_out_form = 1 (conv_out): dw fp32 [nc][wc][3][3] = inv_scale * sum wide[q + tap][wc] * narrow[c][q]
- * narrow_sum (may be NULL): float[nc] plain sums of the narrow tensor (conv_out's bias gradient).
- * partial: float[parts][nc*9*wc + nc] scratch; parts = number of CTAs (grid-stride over image rows). */
+ * narrow_sum (may be NULL): float[nc] inv_scale * plain sums of the narrow tensor (conv_out's bias gradient).
+ * partial: float[parts + 1][nc*9*wc + nc] scratch; parts = number of CTAs (grid-stride over image rows). */
 int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, int32_t h, int32_t w, int32_t wc,
                     int32_t nc, int32_t conv_out_form, float* partial, int32_t parts, const float* inv_scale, float* dw,
                     float* narrow_sum, void* stream);

@@ -157,9 +157,9 @@ def test_gn_bwd_matches_autograd(case):
     dx1 = old1.clone() if acc else None
     dx2 = old2.clone() if (acc and c2) else None
     inv = torch.tensor([0.25], device=d)
-    dx1, dx2, dgamma, dbeta, per_n = ops.gn_bwd(_nhwc(dy), x1, x2, gamma.detach(), beta.detach(), 32, 1e-5, act,
-                                                addend=addend, dx1=dx1, dx2=dx2, acc1=acc, acc2=acc,
-                                                want_colsum=True, inv_scale=inv)
+    dx1, dx2, dgamma, dbeta, per_n, os1, os2 = ops.gn_bwd(_nhwc(dy), x1, x2, gamma.detach(), beta.detach(), 32, 1e-5,
+                                                          act, addend=addend, dx1=dx1, dx2=dx2, acc1=acc, acc2=acc,
+                                                          want_colsum=True, inv_scale=inv, want_osum=True)
     want = _nhwc(dx_ref).float()
     colsum_ref = want.sum(dim=(1, 2))
     if use_add:
@@ -171,6 +171,10 @@ def test_gn_bwd_matches_autograd(case):
     assert _rel(dgamma, 0.25 * dg_ref) < 3e-3
     assert _rel(dbeta, 0.25 * db_ref) < 3e-3
     assert _rel(per_n, colsum_ref) < 5e-3
+    # column sums of the stored gradients (the producer's bias gradient): exactly what a reader of dx would sum
+    assert _rel(os1, dx1.float().sum(dim=(0, 1, 2))) < 1e-4
+    if c2:
+        assert _rel(os2, dx2.float().sum(dim=(0, 1, 2))) < 1e-4
 
 
 @pytest.mark.parametrize("shape", [(2, 256, 16), (1, 1024, 64), (2, 200, 8)])
