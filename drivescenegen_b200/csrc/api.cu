@@ -1,5 +1,6 @@
 // api.cu — error reporting, version, launch accounting.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -16,6 +17,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // measured on B200 (profiles/README.md): no gain — the step is power-capped, idle gaps are not the limiter — so
+    // programmatic dependent launch stays opt-in (DSG_PDL=1)
+    const char* e = getenv("DSG_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 }  // namespace dsg
 
 extern "C" {

@@ -97,6 +97,7 @@ attention_bwd_tc_kernel(const __half* __restrict__ qkv, const __half* __restrict
   uint64_t* bar = &bars[wg];
   uint32_t ph = 0;
   const int nblk = tokens / ABT_KB, ntiles = tokens / 128;
+  pdl_sync();
 
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     const int b = pair / heads, h = pair - b * heads;
@@ -267,8 +268,8 @@ int launch_attention_bwd_tc(const __half* qkv, const __half* o, const __half* do
   const int pairs = n * heads;
   const int grid = pairs < sms ? pairs : sms;
   const float scale = 1.0f / sqrtf(8.0f);
-  attention_bwd_tc_kernel<<<grid, ABT_THREADS, sm, st>>>(qkv, o, dout, lse, dqkv, pairs, tokens, heads, scale,
-                                                         scale * 1.4426950408889634f);
+  launch_k(attention_bwd_tc_kernel, dim3(grid), dim3(ABT_THREADS), sm, st, qkv, o, dout, lse, dqkv, pairs, tokens, heads,
+           scale, scale * 1.4426950408889634f);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention_bwd/tcgen05");
   return DSG_OK;
 }

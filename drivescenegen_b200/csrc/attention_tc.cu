@@ -93,6 +93,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   uint64_t* bar = &bars[wg];
   uint32_t ph = 0;
   const int nkb = tokens / ATC_KB, ntiles = tokens / 128;
+  pdl_sync();
 
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     const int b = pair / heads, h = pair - b * heads;
@@ -260,8 +261,8 @@ int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int h
   }
   const int pairs = n * heads;
   const int grid = pairs < atc_sms() ? pairs : atc_sms();
-  attention_tc_kernel<<<grid, ATC_THREADS, sm, st>>>(qkv, out, pairs, tokens, heads,
-                                                     1.4426950408889634f / sqrtf(8.0f), dbg, lse_out);
+  launch_k(attention_tc_kernel, dim3(grid), dim3(ATC_THREADS), sm, st, qkv, out, pairs, tokens, heads,
+           1.4426950408889634f / sqrtf(8.0f), dbg, lse_out);
   DSG_CUDA_LAUNCH_CHECK("dsg_attention/tcgen05");
   return DSG_OK;
 }

@@ -13,6 +13,29 @@ namespace dsg {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool pdl_enabled();  // api.cu: programmatic dependent launch when DSG_PDL=1 (opt-in)
+
+// Programmatic dependent launch (PDL).  Kernels that call pdl_wait() before their first access to global memory may be
+// launched with launch_k(): the grid is allowed to start (block scheduling, barrier init, TMEM allocation, descriptor
+// prefetch) while the previous kernel of the stream drains, and blocks in pdl_wait() until that kernel has completed and
+// its writes are visible.  Every kernel in a chain waits, so completion is transitive and the semantics are exactly
+// stream order.  pdl_trigger() lets the NEXT kernel's blocks be scheduled as soon as every block of this grid is
+// running.  Works under stream capture (programmatic graph edges).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 #define DSG_CHECK_ARG(cond, ...)       \
   do {                                 \
@@ -37,6 +60,10 @@ __host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { r
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
 // SiLU with ONE MUFU op per element: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (tanh.approx: ~2^-11 relative,
 // the same size as the fp16 rounding of the stored result).  exp + reciprocal would be two MUFU ops, and the
 // GroupNorm+SiLU pass is MUFU-bound before it is HBM-bound at 16 MUFU lanes per SM.

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_in_kernel(const float* __r
                                                              int n, int cin, int h, int wd, int cout) {
   extern __shared__ float sw[];  // [cin*9][cout] then bias[cout]
   const int K = cin * 9;
+  pdl_sync();
   for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
     const int k = i / cout, co = i - k * cout;  // w is [cout][cin][3][3] = [cout][K]
     sw[i] = w[co * K + k];
@@ -163,8 +164,8 @@ int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, i
   if (sm > 48 * 1024) cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   int64_t blocks = ceil_div64(total_q, qpb);
   if (blocks > 148 * 2) blocks = 148 * 2;  // persistent: the weight staging is paid once per block
-  conv_in_kernel<<<(unsigned)blocks, CS_THREADS, sm, (cudaStream_t)stream>>>(
-      x, w, b, (__half*)out_h16, n, cin, h, wd, cout);
+  launch_k(conv_in_kernel, dim3((unsigned)blocks), dim3(CS_THREADS), sm, (cudaStream_t)stream, x, w, b,
+           (__half*)out_h16, n, cin, h, wd, cout);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_in");
   return DSG_OK;
 }

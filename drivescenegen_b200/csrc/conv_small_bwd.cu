@@ -239,8 +239,8 @@ int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, i
   // fixed-order sum over the CTAs' partials into the scratch row that follows them, then the layout change
   const int stride = nc * 9 * wc + nc;
   float* red = partial + (int64_t)parts * stride;
-  reduce_rows_kernel<1><<<ceil_div(stride, 32), 256, 0, st>>>(partial, 1, parts, stride, 0, stride, nullptr, 0, 0,
-                                                              inv_scale, red, nullptr, nullptr);
+  launch_k(reduce_rows_kernel<1>, dim3(ceil_div(stride, 32)), dim3(256), 0, st, (const float*)partial, 1, parts, stride,
+           (int64_t)0, (int64_t)stride, (float*)nullptr, 0, 0, inv_scale, red, (float*)nullptr, (float*)nullptr);
   DSG_CUDA_LAUNCH_CHECK("dsg_small_wgrad/reduce");
   small_wgrad_remap_kernel<<<ceil_div(stride, 256), 256, 0, st>>>(red, nc, wc, conv_out_form ? 0 : 1, dw, narrow_sum);
   DSG_CUDA_LAUNCH_CHECK("dsg_small_wgrad/finalize");

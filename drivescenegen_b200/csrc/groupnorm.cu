@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
   const int V = C >> 3;
   const int ppi = GN_THREADS / V;  // pixel rows per iteration (V <= 256)
   const int n = blockIdx.y, chunk = blockIdx.x;
+  pdl_sync();
   __shared__ float s_part[2][GN_THREADS * 8];
   const int64_t base_px = (int64_t)n * hw;
   if ((int)threadIdx.x < ppi * V) {
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   const int64_t p_begin = (int64_t)blockIdx.x * px_per_cta;
   int64_t p_end = p_begin + px_per_cta;
   if (p_end > hw) p_end = hw;
+  pdl_sync();
   // the first batch of loads does not depend on the statistics: put it in flight before the prologue
   uint4 raw[GN_ILP];
   int64_t p = p_begin + prow;
@@ -203,8 +205,8 @@ int dsg_gn_stats(const void* x, int32_t c, void* stats, int32_t n, int64_t hw, v
   if (chunks > 65535) chunks = 65535;
   const int64_t ppc = ceil_div64(hw, chunks);
   chunks = ceil_div64(hw, ppc);
-  gn_stats_kernel<<<dim3((unsigned)chunks, n), GN_THREADS, 0, (cudaStream_t)stream>>>((const __half*)x, c,
-                                                                                      (long long*)stats, hw, ppc);
+  launch_k(gn_stats_kernel, dim3((unsigned)chunks, n), GN_THREADS, 0, (cudaStream_t)stream, (const __half*)x, c,
+           (long long*)stats, hw, ppc);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_stats");
   return DSG_OK;
 }
@@ -235,10 +237,10 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
   int64_t px_per_cta = ceil_div64(ceil_div64(hw, per_sample), batch_px) * batch_px;
   int64_t ctas = ceil_div64(hw, px_per_cta);
   if (ctas > 65535) { px_per_cta = ceil_div64(hw, 65535); ctas = ceil_div64(hw, px_per_cta); }
-  gn_apply_kernel<<<dim3((unsigned)ctas, n), GN_THREADS, 0, (cudaStream_t)stream>>>(
-      (const __half*)x1, c1, (const long long*)stats1, (const __half*)x2, c2, (const long long*)stats2, gamma, beta,
-      eps, act, (__half*)y, hw, groups, px_per_cta, 1.0 / 16777216.0 / ((double)hw * (double)(C / groups)),
-      1.0 / 1048576.0 / ((double)hw * (double)(C / groups)));
+  launch_k(gn_apply_kernel, dim3((unsigned)ctas, n), GN_THREADS, 0, (cudaStream_t)stream, (const __half*)x1, c1,
+           (const long long*)stats1, (const __half*)x2, c2, (const long long*)stats2, gamma, beta, eps, act, (__half*)y,
+           hw, groups, px_per_cta, 1.0 / 16777216.0 / ((double)hw * (double)(C / groups)),
+           1.0 / 1048576.0 / ((double)hw * (double)(C / groups)));
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_apply");
   return DSG_OK;
 }

@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   int64_t p_end = p_begin + a.px_per_block;
   if (p_end > a.hw) p_end = a.hw;
   int64_t p = p_begin + prow;
+  pdl_sync();
   gn_moments(a, n, s_mean, s_rstd, s_t);
   if (active) {
     float ga[8], yb[8], sA[8], sB[8];
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   constexpr int ILP = 2;
   int64_t p = p_begin + prow;
   const bool want_osum = (from1 ? a.osum1 : a.osum2) != nullptr;
+  pdl_sync();
   gn_moments(a, n, s_mean, s_rstd, s_t);
   {
     const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(GB_THREADS) colsum_h16_kernel(const __half* __
   __shared__ float s_part[GB_THREADS * 8];
   const bool active = (int)threadIdx.x < ppi * V;
   const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
+  pdl_sync();
   if (active) {
     float s[8];
 #pragma unroll
@@ -361,7 +364,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   a.inv_cnt_q = 1.0 / 1048576.0 / ((double)hw * (double)(C / groups));
   cudaStream_t st = (cudaStream_t)stream;
   a.px_per_block = ceil_div64(hw, chunks);
-  gn_bwd_stats_kernel<<<dim3((unsigned)chunks, n), GB_THREADS, 0, st>>>(a);
+  launch_k(gn_bwd_stats_kernel, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
   int64_t ctas = parts;
   if (ctas == 0) {
@@ -371,7 +374,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
     if (ctas > max_ctas) ctas = max_ctas;
   }
   a.px_per_block = ceil_div64(hw, ctas);
-  gn_bwd_apply_kernel<<<dim3((unsigned)ctas, n), GB_THREADS, 0, st>>>(a);
+  launch_k(gn_bwd_apply_kernel, dim3((unsigned)ctas, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/apply");
   return DSG_OK;
 }
@@ -380,9 +383,9 @@ int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c
                       float* dgamma, float* dbeta, void* stream) {
   DSG_CHECK_ARG(partial && dgamma && dbeta && n >= 0 && chunks >= 1 && c > 0, "dsg_gn_bwd_params: bad args");
   // per-sample slot `chunks` of every sample holds (sum g, sum g * xh) per channel: d beta, d gamma
-  reduce_rows_kernel<2><<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(
-      partial + (int64_t)chunks * c * 2, n, 1, c, (int64_t)(chunks + 1) * c * 2, 0, nullptr, 0, 0, inv_scale, dbeta,
-      nullptr, dgamma);
+  launch_k(reduce_rows_kernel<2>, dim3(ceil_div(c, 32)), dim3(256), 0, (cudaStream_t)stream,
+           partial + (int64_t)chunks * c * 2, n, 1, c, (int64_t)(chunks + 1) * c * 2, (int64_t)0, (float*)nullptr, 0, 0,
+           inv_scale, dbeta, (float*)nullptr, dgamma);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd_params");
   return DSG_OK;
 }
@@ -392,7 +395,8 @@ int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32
                 "dsg_colsum_h16: bad args");
   DSG_CHECK_ARG((uintptr_t)x % 16 == 0, "dsg_colsum_h16: unaligned pointer");
   const int64_t rpb = ceil_div64(rows > 0 ? rows : 1, parts);
-  colsum_h16_kernel<<<parts, GB_THREADS, 0, (cudaStream_t)stream>>>((const __half*)x, rows, c, partial, rpb);
+  launch_k(colsum_h16_kernel, dim3(parts), dim3(GB_THREADS), 0, (cudaStream_t)stream, (const __half*)x, rows, c, partial,
+           rpb);
   DSG_CUDA_LAUNCH_CHECK("dsg_colsum_h16");
   return DSG_OK;
 }
@@ -400,8 +404,8 @@ int dsg_colsum_h16(const void* x, int64_t rows, int32_t c, float* partial, int32
 int dsg_colsum_finalize(const float* partial, int32_t n, int32_t parts, int32_t c, float* per_n, int32_t per_n_stride,
                         int32_t per_n_off, const float* inv_scale, float* total, float* total2, void* stream) {
   DSG_CHECK_ARG(partial && n >= 0 && parts >= 1 && c > 0, "dsg_colsum_finalize: bad args");
-  reduce_rows_kernel<1><<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(
-      partial, n, parts, c, (int64_t)parts * c, c, per_n, per_n_stride, per_n_off, inv_scale, total, total2, nullptr);
+  launch_k(reduce_rows_kernel<1>, dim3(ceil_div(c, 32)), dim3(256), 0, (cudaStream_t)stream, partial, n, parts, c,
+           (int64_t)parts * c, (int64_t)c, per_n, per_n_stride, per_n_off, inv_scale, total, total2, (float*)nullptr);
   DSG_CUDA_LAUNCH_CHECK("dsg_colsum_finalize");
   return DSG_OK;
 }

@@ -108,6 +108,7 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  pdl_sync();  // setup above overlaps the previous kernel's tail
 
   // Roles run warp-uniform; only the TMA / tcgen05 instructions are under elect_one_sync() (see common.cuh).
   if (warp == 0) {
@@ -463,7 +464,7 @@ static int launch_igemm(const IgPlan& plan_in, cudaStream_t st) {
     attr_set = true;
   }
   int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  igemm_kernel<BLOCK_N><<<(unsigned)grid, IG_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+  launch_k(igemm_kernel<BLOCK_N>, dim3((unsigned)grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, maps, p);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv/igemm");
   return DSG_OK;
 }

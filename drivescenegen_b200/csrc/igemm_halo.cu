@@ -216,6 +216,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  pdl_sync();  // everything above overlaps the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
@@ -492,14 +493,16 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
     cfg.blockDim = dim3(HL_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<BLOCK_N, MT, CG>, maps, p);
     if (e != cudaSuccess) { set_error("igemm_halo (CTA pair): launch: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
   } else {
-    igemm_halo_kernel<BLOCK_N, MT, CG><<<(unsigned)grid, HL_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+    launch_k(igemm_halo_kernel<BLOCK_N, MT, CG>, dim3((unsigned)grid), dim3(HL_THREADS), Cfg::SMEM_BYTES, st, maps, p);
   }
   DSG_CUDA_LAUNCH_CHECK("dsg_conv/igemm_halo");
   return DSG_OK;

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool ok = c < C;
+  pdl_sync();
   float tot[COMPS];
 #pragma unroll
   for (int q = 0; q < COMPS; ++q) tot[q] = 0.f;

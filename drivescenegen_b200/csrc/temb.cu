@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_mlp_kernel(const float* __res
   float* e = sm;               // [2*half]
   float* h1 = sm + 2 * half;   // [hidden]
   const int b = blockIdx.x, in_dim = 2 * half;
+  pdl_sync();
   const float tv = t[b];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float arg = __fmul_rn(tv, freqs[i]);
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(TE_THREADS) temb_proj_kernel(const float* __re
   extern __shared__ float sm[];  // [TP_BT][hidden]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int r = blockIdx.x * nwarp + warp;
+  pdl_sync();
   for (int b0 = 0; b0 < batch; b0 += TP_BT) {
     const int nb = min(TP_BT, batch - b0);
     __syncthreads();
@@ -112,15 +114,15 @@ extern "C" int dsg_time_embed_ex(const float* t, const float* freqs, int32_t hal
                 "dsg_time_embed: bad sizes");
   if (batch == 0) return DSG_OK;
   const size_t sm1 = (size_t)(2 * half + hidden) * sizeof(float);
-  temb_mlp_kernel<<<batch, TE_THREADS, sm1, (cudaStream_t)stream>>>(t, freqs, half, flip_sin_to_cos, w1t, b1, w2t,
-                                                                    b2, hidden, emb_ws, saved);
+  launch_k(temb_mlp_kernel, dim3(batch), dim3(TE_THREADS), sm1, (cudaStream_t)stream, t, freqs, half, flip_sin_to_cos,
+           w1t, b1, w2t, b2, hidden, emb_ws, saved);
   DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/mlp");
   const size_t sm2 = (size_t)TP_BT * hidden * sizeof(float);
   if (sm2 > 48 * 1024)
     cudaFuncSetAttribute(temb_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
   const int rows_per_cta = TE_THREADS / 32;
-  temb_proj_kernel<<<ceil_div(proj_total, rows_per_cta), TE_THREADS, sm2, (cudaStream_t)stream>>>(
-      emb_ws, wp, bp, hidden, proj_total, out, batch);
+  launch_k(temb_proj_kernel, dim3(ceil_div(proj_total, rows_per_cta)), dim3(TE_THREADS), sm2, (cudaStream_t)stream,
+           (const float*)emb_ws, wp, bp, hidden, proj_total, out, batch);
   DSG_CUDA_LAUNCH_CHECK("dsg_time_embed/proj");
   return DSG_OK;
 }

@@ -127,6 +127,7 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
+  pdl_sync();  // setup above overlaps the previous kernel's tail
 
   int stage_bytes_tx = p.a_bytes;
   for (int b = 0; b < G.nbox; ++b) stage_bytes_tx += G.box[b].bytes;
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            float* __restrict__ out, int accumulate) {
   const int KK = fold_up ? 9 : ktaps;
   const int64_t total = (int64_t)co_count * KK * ci;
+  pdl_sync();
   const float s = inv_scale ? *inv_scale : 1.0f;
   const int64_t split_stride = (int64_t)co * ktaps * ci;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -507,13 +509,12 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
     attr_set = true;
   }
-  wgrad_kernel<<<dim3((unsigned)splits, (unsigned)items), WG_THREADS, smem_bytes, st>>>(maps, p);
+  launch_k(wgrad_kernel, dim3((unsigned)splits, (unsigned)items), dim3(WG_THREADS), smem_bytes, st, maps, p);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/tcgen05");
   int64_t blocks = ceil_div64(out_elems, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.ws, splits, a->cout, p.ktaps, a->cin, a->mode == 2 ? 1 : 0, 0,
-                                                       a->cout, a->ci_total, a->ci_off, a->inv_scale, a->grad,
-                                                       a->accumulate);
+  launch_k(wgrad_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const float*)p.ws, splits, a->cout, p.ktaps,
+           a->cin, a->mode == 2 ? 1 : 0, 0, a->cout, a->ci_total, a->ci_off, a->inv_scale, a->grad, a->accumulate);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/reduce");
   return DSG_OK;
 }
