@@ -36,6 +36,9 @@ class ConvArgs(C.Structure):
         ("out_nchw_f32", C.c_void_p),
         ("cout_real", C.c_int32),
         ("out_stats", C.c_void_p),
+        ("x2", C.c_void_p),
+        ("cin1", C.c_int32),
+        ("gn_coef", C.c_void_p),
     ]
 
 
@@ -85,6 +88,8 @@ SIGNATURES = {
     "dsg_gn_stats": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
     "dsg_gn_apply": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _i64, _i32, _p]),
     "dsg_conv": (C.c_int, [C.POINTER(ConvArgs), _p]),
+    "dsg_conv_gn_fusable": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "dsg_gn_coef": (C.c_int, [_i32, _p, _i32, _p, _p, _p, _f, _p, _i32, _i64, _i32, _p]),
     "dsg_packed_k": (_i64, [_i32, _i32, _i32]),
     "dsg_packed_rows": (_i64, [_i32, _i32]),
     "dsg_pack_conv_weight": (C.c_int, [_i32, _p, _i32, _i32, _p, _i32, _p, _p]),

@@ -185,11 +185,67 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __re
   }
 }
 
+// ------------------------------------------------------------------ coefficients for the fused (in-conv) form
+// grid = n; coef[n][c] = (a / 2, b / 2), GroupNorm(x) = a x + b.  Same statistics arithmetic as gn_apply_kernel.
+__global__ void __launch_bounds__(GN_THREADS) gn_coef_kernel(int c1, const long long* __restrict__ st1, int c2,
+                                                             const long long* __restrict__ st2,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             float2* __restrict__ coef, int groups, double inv_cnt_s,
+                                                             double inv_cnt_q) {
+  const int C = c1 + c2, cpg = C / groups;
+  const int n = blockIdx.x;
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  __shared__ unsigned long long s_t[GN_MAX_GROUPS][2];
+  pdl_sync();
+  if ((int)threadIdx.x < groups) { s_t[threadIdx.x][0] = 0ull; s_t[threadIdx.x][1] = 0ull; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const longlong2 tv = *reinterpret_cast<const longlong2*>(
+        c < c1 ? st1 + ((int64_t)n * c1 + c) * 2 : st2 + ((int64_t)n * c2 + (c - c1)) * 2);
+    if (tv.x != 0 || tv.y != 0) {
+      atomicAdd(&s_t[c / cpg][0], (unsigned long long)tv.x);
+      atomicAdd(&s_t[c / cpg][1], (unsigned long long)tv.y);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const double mg = (double)(long long)s_t[g][0] * inv_cnt_s;
+    double vg = (double)(long long)s_t[g][1] * inv_cnt_q - mg * mg;
+    if (vg < 0.0) vg = 0.0;
+    s_mean[g] = (float)mg;
+    s_rstd[g] = rsqrtf((float)vg + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    const int g = c / cpg;
+    const float a = gamma[c] * s_rstd[g];
+    const float b = beta[c] - s_mean[g] * a;
+    coef[(int64_t)n * C + c] = make_float2(0.5f * a, 0.5f * b);
+  }
+}
+
 }  // namespace dsg
 
 using namespace dsg;
 
 extern "C" {
+
+int dsg_gn_coef(int32_t c1, const void* stats1, int32_t c2, const void* stats2, const float* gamma, const float* beta,
+                float eps, float* coef, int32_t n, int64_t hw, int32_t groups, void* stream) {
+  DSG_CHECK_ARG(stats1 && c1 > 0 && (stats2 == nullptr) == (c2 == 0) && c2 >= 0, "dsg_gn_coef: stats / channel mismatch");
+  const int C = c1 + c2;
+  DSG_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "dsg_gn_coef: bad groups %d for C=%d", groups, C);
+  DSG_CHECK_ARG(gamma && beta && coef && n >= 0 && hw > 0, "dsg_gn_coef: bad args");
+  DSG_CHECK_ARG(((uintptr_t)stats1 | (uintptr_t)stats2 | (uintptr_t)coef) % 16 == 0, "dsg_gn_coef: unaligned pointer");
+  if (n == 0) return DSG_OK;
+  launch_k(gn_coef_kernel, dim3(n), dim3(GN_THREADS), 0, (cudaStream_t)stream, c1, (const long long*)stats1, c2,
+           (const long long*)stats2, gamma, beta, eps, (float2*)coef, groups,
+           1.0 / 16777216.0 / ((double)hw * (double)(C / groups)), 1.0 / 1048576.0 / ((double)hw * (double)(C / groups)));
+  DSG_CUDA_LAUNCH_CHECK("dsg_gn_coef");
+  return DSG_OK;
+}
 
 int dsg_gn_stats(const void* x, int32_t c, void* stats, int32_t n, int64_t hw, void* stream) {
   DSG_CHECK_ARG(x && stats && c > 0 && c % 8 == 0 && c <= GN_MAX_C, "dsg_gn_stats: null pointer or bad c=%d", c);

@@ -521,6 +521,15 @@ int dsg_pack_conv_weights_batched(const dsg_pack_job* jobs_dev, int32_t njobs, i
   return DSG_OK;
 }
 
+int dsg_conv_gn_fusable(int32_t mode, int32_t h, int32_t w, int32_t cin, int32_t cin1, int32_t cout) {
+  if (mode != 0 || cin % 64 || cin1 % 64 || cin1 <= 0 || cin1 > cin) return 0;
+  if (!(cout == 16 || cout % 64 == 0)) return 0;
+  const int tw = w >= 16 ? 16 : (w >= 8 ? 8 : 0);
+  if (!tw) return 0;
+  const int mt = (cout % 256 == 0) ? 1 : 2;   // MT of the kernel variant dsg_conv picks
+  return h >= mt * (128 / tw) + 2 ? 1 : 0;
+}
+
 int dsg_conv(const dsg_conv_args* a, void* stream) {
   DSG_CHECK_ARG(a != nullptr, "dsg_conv: args is null");
   IgPlan p;
@@ -530,6 +539,7 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->impl == 1) {
     DSG_CHECK_ARG(a->out && !a->out_nchw_f32, "dsg_conv: the cross-check kernel writes the h16 NHWC output only");
+    DSG_CHECK_ARG(!a->gn_coef && !a->x2, "dsg_conv: the cross-check kernel has no fused GroupNorm input");
     p.n_blocks = 1;
     const int64_t total = (int64_t)p.phases * p.N * p.OH * p.OW * p.cout;
     int64_t blocks = ceil_div64(total, 256);
@@ -539,6 +549,15 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
     return DSG_OK;
   }
   DSG_CHECK_ARG(a->impl == 0 || (a->impl >= 2 && a->impl <= 4), "dsg_conv: bad impl %d", a->impl);
+  if (a->gn_coef) {
+    DSG_CHECK_ARG(a->mode == 0 && a->impl != 2, "dsg_conv: fused GroupNorm input needs mode 0 on the halo-reuse kernels");
+    DSG_CHECK_ARG((a->x2 == nullptr) ? (a->cin1 == a->cin || a->cin1 == 0)
+                                     : (a->cin1 > 0 && a->cin1 < a->cin && a->cin1 % 64 == 0),
+                  "dsg_conv: bad cin1 %d for cin %d", a->cin1, a->cin);
+    DSG_CHECK_ARG(((uintptr_t)a->gn_coef | (uintptr_t)a->x2) % 16 == 0, "dsg_conv: gn_coef / x2 must be 16-byte aligned");
+  } else {
+    DSG_CHECK_ARG(a->x2 == nullptr, "dsg_conv: x2 is only valid together with gn_coef");
+  }
   if (a->out_nchw_f32) {
     DSG_CHECK_ARG(a->mode == 0 && a->cout == 16 && a->cout_real >= 1 && a->cout_real <= 16 && !a->residual &&
                       !a->csc1 && a->impl != 2 && (uintptr_t)a->out_nchw_f32 % 4 == 0,
@@ -562,7 +581,10 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
       rc = launch_halo_conv(a, bn, 0, st);
       if (rc != DSG_HALO_SKIP) return rc;
     }
-    if (a->impl >= 3) { set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel"); return DSG_ERR_UNSUPPORTED; }
+    if (a->impl >= 3 || a->gn_coef) {
+      set_error("dsg_conv: shape/mode not covered by the halo-reuse kernel");
+      return DSG_ERR_UNSUPPORTED;
+    }
   }
   switch (bn) {
     case 64: return launch_igemm<64>(p, st);

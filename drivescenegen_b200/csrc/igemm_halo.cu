@@ -20,13 +20,17 @@
 namespace dsg {
 
 constexpr int HL_THREADS = 192;
-constexpr int HL_MAX_GROUPS = 5;
-constexpr int HL_MAX_MAPS = 3;
+constexpr int HL_THREADS_FUSED = 256;  // + two GroupNorm/SiLU transform warps (256 threads keep 255 registers each)
+constexpr int HL_XF_THREADS = 64;
+constexpr int HL_MAX_GROUPS = 8;
+constexpr int HL_MAX_MAPS = 4;
 
 struct HlGroup {
   int map;         // which activation tensor map (source + box height)
   int dx, dy0;     // box origin relative to the tile origin (phase offset added at run time)
   int nchunks;     // 64-channel chunks of this source
+  int chunk_off;   // first 64-channel chunk of this source inside the (concatenated) conv input
+  int transform;   // fused GroupNorm + SiLU: the box holds RAW values and is normalised in shared memory
   int ntaps;       // taps served by one box (<= 3)
   int row_off[3];  // first box row of tap t
   int kb_base[3];  // weight k-block (64 columns each) of (tap t, chunk 0)
@@ -50,6 +54,9 @@ struct HlPlan {
   const float* temb;
   int temb_stride, temb_off;
   long long* stats;    // optional per-channel GroupNorm totals of the output: int64 [N][cout][2] (groupnorm.cu)
+  const float2* coef;  // fused GroupNorm + SiLU of the input: [N][cin_main] (a / 2, b / 2); act = h + h tanh(h), h = a x / 2 + b / 2
+  int cin_main;        // channels of the (concatenated) 3x3 input
+  int IH, IW;          // extents of the 3x3 input (masking of the zero padding under the fused transform)
   int64_t total_tiles;
 };
 
@@ -74,7 +81,7 @@ struct HlCfg {
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
   static constexpr int SMEM_BYTES =
       RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
-  static_assert(2 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
+  static_assert(3 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
 };
@@ -167,8 +174,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int BLOCK_N, int MT, int CG>
-__global__ void __launch_bounds__(HL_THREADS, 1)
+// FUSE = 1: the GroupNorm + SiLU that precedes the conv (ResnetBlock2D norm1/norm2 + nonlinearity, conv_norm_out +
+// conv_act) is applied to the activation boxes IN SHARED MEMORY by four extra warps between the TMA landing and the
+// MMA reading (per-(sample, channel) coefficients from dsg_gn_coef, packed half2 math, padding left at zero): the
+// normalised tensor never exists in HBM — one read + one write of every activation less per GroupNorm.
+template <int BLOCK_N, int MT, int CG, int FUSE>
+__global__ void __launch_bounds__(FUSE ? HL_THREADS_FUSED : HL_THREADS, 1)
 igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ HlPlan p) {
   using Cfg = HlCfg<BLOCK_N, MT, CG>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB;
@@ -185,7 +196,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   uint64_t* b_empty = b_full + NB;
   uint64_t* tfull = b_empty + NB;   // [2]
   uint64_t* tempty = tfull + 2;     // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* a_land = tempty + 2;    // [NA] (FUSE only): raw box landed in THIS CTA's shared memory
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_land + NA);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -205,6 +217,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], CG); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    if constexpr (FUSE != 0)
+      for (int i = 0; i < NA; ++i) mbar_init(&a_land[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -231,7 +245,13 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
           const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
           for (int c = 0; c < G.nchunks; ++c) {
             mbar_wait(&a_empty[as], aph ^ 1);
-            if (elect_one_sync()) {
+            if (FUSE != 0 && G.transform) {
+              // raw box -> this CTA's own "landed" barrier; the transform warps publish it to the MMA issuer
+              if (elect_one_sync()) {
+                mbar_arrive_expect_tx(&a_land[as], (uint32_t)G.bytes);
+                tma_load_4d(a_ring + as * Cfg::A_SLOT, &maps.a[G.map], &a_land[as], c * IG_BLOCK_K, wx, hy, tc.n);
+              }
+            } else if (elect_one_sync()) {
               if constexpr (CG == 2) {
                 const uint32_t fb = mapa_u32(&a_full[as], 0);
                 mbar_arrive_expect_tx_cluster(fb, (uint32_t)G.bytes);
@@ -246,13 +266,14 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
             for (int tp = 0; tp < G.ntaps; ++tp) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               if (elect_one_sync()) {
+                const int kcol = (G.kb_base[tp] + G.chunk_off + c) * IG_BLOCK_K;
                 if constexpr (CG == 2) {
                   const uint32_t fb = mapa_u32(&b_full[bs], 0);
                   mbar_arrive_expect_tx_cluster(fb, (uint32_t)Cfg::B_SLOT);
-                  tma_load_2d_cg2(b_ring + bs * Cfg::B_SLOT, &maps.b, fb, (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+                  tma_load_2d_cg2(b_ring + bs * Cfg::B_SLOT, &maps.b, fb, kcol, brow);
                 } else {
                   mbar_arrive_expect_tx(&b_full[bs], (uint32_t)Cfg::B_SLOT);
-                  tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], (G.kb_base[tp] + c) * IG_BLOCK_K, brow);
+                  tma_load_2d(b_ring + bs * Cfg::B_SLOT, &maps.b, &b_full[bs], kcol, brow);
                 }
               }
               __syncwarp();
@@ -318,6 +339,70 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
           }
         }
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else if (FUSE != 0 && warp >= 6) {
+    // ===================================================== GroupNorm + SiLU transform warps (FUSE only)
+    // A box is [pixel][64 channels] in 128-byte rows, 16-byte chunks XOR-swizzled with (pixel & 7).  Thread tt walks the
+    // chunks tt, tt + 64, ...: its pixel index advances by 8 each step, so it always meets the SAME logical channel
+    // group lc — its eight (a, b) pairs stay in registers for the whole box.
+    const int tt = threadIdx.x - 192;
+    const int lc = (tt & 7) ^ ((tt >> 3) & 7);
+    int as = 0;
+    uint32_t land_ph = 0;  // per-slot phase bits: a_land[s] only advances when slot s carries a TRANSFORMED box
+    for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
+      const HlTile tc = hl_decode(p, t, CG, (int)rank);
+      for (int g = 0; g < p.ngroups; ++g) {
+        const HlGroup& G = p.grp[g];
+        if (!G.transform) {
+          as = (as + G.nchunks) % NA;
+          continue;
+        }
+        const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
+        const int nchk = G.bytes >> 4;  // 16-byte chunks in the box
+        for (int c = 0; c < G.nchunks; ++c) {
+          const float4* cf = reinterpret_cast<const float4*>(p.coef + (int64_t)tc.n * p.cin_main +
+                                                             (G.chunk_off + c) * 64 + lc * 8);
+          __half2 a2[4], b2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldg(cf + j);  // (a0, b0, a1, b1)
+            a2[j] = __floats2half2_rn(v.x, v.z);
+            b2[j] = __floats2half2_rn(v.y, v.w);
+          }
+          mbar_wait(&a_land[as], (land_ph >> as) & 1u);
+          land_ph ^= 1u << as;
+          uint8_t* box = a_ring + as * Cfg::A_SLOT;
+#pragma unroll 4
+          for (int q = tt; q < nchk; q += HL_XF_THREADS) {
+            const int r = q >> 3;
+            const int y = hy + (r >> p.tw_shift), x = wx + (r & (p.TW - 1));
+            if (y >= 0 && y < p.IH && x >= 0 && x < p.IW) {  // padding stays zero
+              uint4 v = *reinterpret_cast<uint4*>(box + (size_t)q * 16);
+              __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __half2 h = __hfma2(hv[j], a2[j], b2[j]);
+                uint32_t hu = *reinterpret_cast<const uint32_t*>(&h), tu;
+                asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+                hv[j] = __hfma2(h, *reinterpret_cast<const __half2*>(&tu), h);
+              }
+              *reinterpret_cast<uint4*>(box + (size_t)q * 16) = v;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA (async proxy)
+          asm volatile("bar.sync 2, 64;" ::: "memory");
+          if (tt == 0) {
+            if constexpr (CG == 2) {
+              // plain arrive: each CTA's tensor core reads its OWN shared memory for A, and this CTA's writes were made
+              // visible to its async proxy by the fence above (a cluster-scope release costs a full memory barrier)
+              mbar_arrive_cluster(mapa_u32(&a_full[as], 0));
+            } else {
+              mbar_arrive(&a_full[as]);
+            }
+          }
+          if (++as == NA) as = 0;
+        }
       }
     }
   } else {
@@ -408,7 +493,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
 }
 
 // ------------------------------------------------------------------ host side
-template <int BLOCK_N, int MT, int CG>
+template <int BLOCK_N, int MT, int CG, int FUSE>
 static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   using Cfg = HlCfg<BLOCK_N, MT, CG>;
   HlPlan p;
@@ -419,26 +504,39 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   const int th = MT * (128 / tw);
   const int halo = a->mode == 0 ? 2 : 1;
   if (oh < th + halo) return DSG_HALO_SKIP;  // keep every TMA box inside the tensor extents
+  if (FUSE != 0 && a->mode != 0) return DSG_HALO_SKIP;
   p.N = a->n; p.OH = oh; p.OW = ow; p.TW = tw; p.tw_shift = sh; p.TH = th;
   p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th * CG);  // a CTA pair stacks its two tiles vertically
   p.cout = a->cout; p.n_blocks = a->cout / BLOCK_N;
   const int cin_chunks = a->cin / 64;
+  // the 3x3 input is one tensor, or (fused GroupNorm form) the channel concatenation of two raw tensors
+  const int cin1 = (FUSE != 0 && a->x2) ? a->cin1 : a->cin;
+  const int nsrc = cin1 < a->cin ? 2 : 1;
+  const int src_chunks[2] = {cin1 / 64, (a->cin - cin1) / 64};
+  const int src_map[2] = {0, 3};
   HlMaps maps;
   memset(&maps, 0, sizeof(maps));
-  IgSrc src0 = dense_src(a->x, a->cin, a->h, a->w);
-  int rc = make_map_a(&maps.a[0], src0, a->n, tw, th + halo);
+  int rc = make_map_a(&maps.a[0], dense_src(a->x, cin1, a->h, a->w), a->n, tw, th + halo);
   if (rc) return rc;
+  if (nsrc == 2) {
+    rc = make_map_a(&maps.a[3], dense_src(a->x2, a->cin - cin1, a->h, a->w), a->n, tw, th + halo);
+    if (rc) return rc;
+  }
   int64_t k_total;
   if (a->mode == 0) {
     p.phases = 1; p.omul = 1;
     for (int dx = -1; dx <= 1; ++dx) {
-      HlGroup& G = p.grp[p.ngroups++];
-      G.map = 0; G.dx = dx; G.dy0 = -1; G.nchunks = cin_chunks; G.ntaps = 3;
-      for (int dy = -1; dy <= 1; ++dy) {
-        G.row_off[dy + 1] = dy + 1;
-        G.kb_base[dy + 1] = ((dy + 1) * 3 + (dx + 1)) * cin_chunks;
+      for (int s = 0; s < nsrc; ++s) {
+        HlGroup& G = p.grp[p.ngroups++];
+        G.map = src_map[s]; G.dx = dx; G.dy0 = -1; G.nchunks = src_chunks[s]; G.ntaps = 3;
+        G.chunk_off = s == 0 ? 0 : src_chunks[0];
+        G.transform = FUSE;
+        for (int dy = -1; dy <= 1; ++dy) {
+          G.row_off[dy + 1] = dy + 1;
+          G.kb_base[dy + 1] = ((dy + 1) * 3 + (dx + 1)) * cin_chunks;
+        }
+        G.bytes = (th + 2) * tw * 128;
       }
-      G.bytes = (th + 2) * tw * 128;
     }
     int kb = 9 * cin_chunks;
     const void* scp[2] = {a->sc1, a->sc2};
@@ -450,6 +548,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
       if (rc) return rc;
       HlGroup& G = p.grp[p.ngroups++];
       G.map = 1 + s; G.dx = 0; G.dy0 = 0; G.nchunks = scc[s] / 64; G.ntaps = 1;
+      G.chunk_off = 0; G.transform = 0;
       G.row_off[0] = 0; G.kb_base[0] = kb;
       G.bytes = th * tw * 128;
       kb += scc[s] / 64;
@@ -460,6 +559,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
     for (int j = 0; j < 2; ++j) {
       HlGroup& G = p.grp[p.ngroups++];
       G.map = 0; G.dx = j - 1; G.dy0 = -1; G.nchunks = cin_chunks; G.ntaps = 2;
+      G.chunk_off = 0; G.transform = 0;
       for (int i = 0; i < 2; ++i) {
         G.row_off[i] = i;
         G.kb_base[i] = (i * 2 + j) * cin_chunks;
@@ -476,21 +576,23 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.out_f32 = (float*)a->out_nchw_f32; p.cout_real = a->cout_real;
   p.bias = a->bias; p.temb = a->temb; p.temb_stride = a->temb_stride; p.temb_off = a->temb_off;
   p.stats = (long long*)a->out_stats;
+  p.coef = (const float2*)a->gn_coef; p.cin_main = a->cin; p.IH = a->h; p.IW = a->w;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT, CG>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
     attr_set = true;
   }
+  const int threads = FUSE ? HL_THREADS_FUSED : HL_THREADS;
   const int64_t slots = num_sms() / CG;  // CTAs, or CTA pairs
   const int64_t grid = (p.total_tiles < slots ? p.total_tiles : slots) * CG;
   if constexpr (CG == 2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(HL_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -499,10 +601,10 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<BLOCK_N, MT, CG>, maps, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>, maps, p);
     if (e != cudaSuccess) { set_error("igemm_halo (CTA pair): launch: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
   } else {
-    launch_k(igemm_halo_kernel<BLOCK_N, MT, CG>, dim3((unsigned)grid), dim3(HL_THREADS), Cfg::SMEM_BYTES, st, maps, p);
+    launch_k(igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>, dim3((unsigned)grid), dim3(threads), Cfg::SMEM_BYTES, st, maps, p);
   }
   DSG_CUDA_LAUNCH_CHECK("dsg_conv/igemm_halo");
   return DSG_OK;
@@ -510,19 +612,36 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
 
 int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStream_t st) {
   if (a->mode != 0 && a->mode != 2) return DSG_HALO_SKIP;
+  if (a->gn_coef) {  // fused GroupNorm + SiLU on the input (mode 0 only)
+    if (cta_pair) {
+      switch (block_n) {
+        case 64: return launch_halo<64, 2, 2, 1>(a, st);
+        case 128: return launch_halo<128, 2, 2, 1>(a, st);
+        case 256: return launch_halo<256, 1, 2, 1>(a, st);
+        default: return DSG_HALO_SKIP;
+      }
+    }
+    switch (block_n) {
+      case 16: return launch_halo<16, 2, 1, 1>(a, st);
+      case 64: return launch_halo<64, 2, 1, 1>(a, st);
+      case 128: return launch_halo<128, 2, 1, 1>(a, st);
+      case 256: return launch_halo<256, 1, 1, 1>(a, st);
+      default: return DSG_HALO_SKIP;
+    }
+  }
   if (cta_pair) {
     switch (block_n) {
-      case 64: return launch_halo<64, 2, 2>(a, st);
-      case 128: return launch_halo<128, 2, 2>(a, st);
-      case 256: return launch_halo<256, 1, 2>(a, st);
+      case 64: return launch_halo<64, 2, 2, 0>(a, st);
+      case 128: return launch_halo<128, 2, 2, 0>(a, st);
+      case 256: return launch_halo<256, 1, 2, 0>(a, st);
       default: return DSG_HALO_SKIP;
     }
   }
   switch (block_n) {
-    case 16: return launch_halo<16, 2, 1>(a, st);
-    case 64: return launch_halo<64, 2, 1>(a, st);
-    case 128: return launch_halo<128, 2, 1>(a, st);
-    case 256: return launch_halo<256, 1, 1>(a, st);
+    case 16: return launch_halo<16, 2, 1, 0>(a, st);
+    case 64: return launch_halo<64, 2, 1, 0>(a, st);
+    case 128: return launch_halo<128, 2, 1, 0>(a, st);
+    case 256: return launch_halo<256, 1, 1, 0>(a, st);
     default: return DSG_HALO_SKIP;
   }
 }

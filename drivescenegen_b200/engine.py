@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -73,6 +74,13 @@ class UNetEngine:
         self._stage: Dict[str, torch.Tensor] = {}
         self._aliased = set()
         self._jobs, self._job_keep, self._jobs_uploaded = [], [], None
+        # inference: GroupNorm + SiLU applied inside the consuming conv (dsg_conv gn_coef) wherever the shape allows
+        # GroupNorm + SiLU applied inside the consuming conv (dsg_conv gn_coef).  Measured on B200 (profiles/README.md): a
+        # LOSS — the conv mainloop already runs at the shared-memory bandwidth limit and the in-place transform of every
+        # box (three times per element: one box per column shift) adds smem traffic and one MUFU per element, so the
+        # convs slow down by more than the removed GroupNorm pass costs.  Kept as an opt-in for experiments:
+        # DSG_FUSE_GN = 0 (default) never, 1 = convs with 256-wide tiles only, 2 = wherever the kernel supports it.
+        self.fuse_gn = int(os.environ.get("DSG_FUSE_GN", "0"))
         self.train_packs = False  # also pack the data-gradient forms of every conv weight (training path)
         self.train_programs: Dict[Tuple[int, int, int, int], object] = {}
         self._build_topology()
@@ -402,6 +410,7 @@ class _Program:
         self.out_ptr = C.c_void_p(0)
         self.cin = int(eng.cfg.get("in_channels", 3))
         self.cout = int(eng.cfg.get("out_channels", 3))
+        self.fuse_gn = getattr(self, "fuse_gn", True)   # the training program keeps the normalised tensors: no fusion
         # pass 1 sizes the shared temporaries (so no buffer is outgrown mid-program), pass 2 emits the ops
         self._measure: Optional[Dict[Tuple[str, torch.dtype], int]] = {}
         self._stats_off = 0
@@ -453,16 +462,15 @@ class _Program:
         self.ops.append(fn)
         self.op_info.append((name, meta))
 
-    def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out, st1=None, st2=None):
-        """GroupNorm(+SiLU) of cat(x1, x2); the statistics were accumulated by whoever produced x1 / x2."""
+    def _gn_stats_for(self, x1, c1, x2, c2, hw, st1=None, st2=None):
+        """the statistics a GroupNorm over cat(x1, x2) reads: accumulated by whoever produced x1 / x2, or — odd group
+        sizes, where the conv epilogues' channel-pair totals do not line up with the groups — one extra read."""
         eng, lib, b = self.eng, self.lib, self.b
         npx = hw[0] * hw[1]
         st1 = st1 if st1 is not None else self.stats_of[x1.data_ptr()]
         if x2 is not None and st2 is None:
             st2 = self.stats_of[x2.data_ptr()]
         if ((c1 + c2) // eng.groups) % 2:
-            # odd group size: the conv epilogues' channel-pair totals do not line up with the groups, so take
-            # per-channel statistics with one extra read of each source instead
             srcs = [(x1, c1)] + ([(x2, c2)] if x2 is not None else [])
             fresh = []
             for xs, cs in srcs:
@@ -472,6 +480,13 @@ class _Program:
                 self._emit("gn_stats", {"bytes": b * npx * cs * 2},
                            lambda st, a=ga: check(lib.dsg_gn_stats(*a, st), "gn_stats"))
             st1, st2 = fresh[0], (fresh[1] if len(fresh) > 1 else None)
+        return st1, st2
+
+    def _gn(self, x1, c1, x2, c2, hw, gname, bname, act, out, st1=None, st2=None):
+        """GroupNorm(+SiLU) of cat(x1, x2); the statistics were accumulated by whoever produced x1 / x2."""
+        eng, lib, b = self.eng, self.lib, self.b
+        npx = hw[0] * hw[1]
+        st1, st2 = self._gn_stats_for(x1, c1, x2, c2, hw, st1, st2)
         g, bt = eng.weights[gname], eng.weights[bname]
         a2 = (_p(x1), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps, act,
               out.data_ptr(), b, npx, eng.groups)
@@ -479,8 +494,29 @@ class _Program:
         self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
         return st1, st2
 
+    def _gn_coef(self, x1, c1, x2, c2, hw, gname, bname, st1=None, st2=None) -> torch.Tensor:
+        """fused form: only the per-(sample, channel) coefficients are computed here; the consuming conv applies
+        GroupNorm + SiLU to its activation boxes in shared memory (dsg_conv gn_coef)."""
+        eng, lib, b = self.eng, self.lib, self.b
+        npx = hw[0] * hw[1]
+        st1, st2 = self._gn_stats_for(x1, c1, x2, c2, hw, st1, st2)
+        coef = self._tmp_raw("gn_coef", b * (c1 + c2) * 2, torch.float32)
+        g, bt = eng.weights[gname], eng.weights[bname]
+        a2 = (c1, st1.data_ptr(), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps, coef.data_ptr(), b, npx,
+              eng.groups)
+        self._emit("gn_coef", {"bytes": b * (c1 + c2) * 24}, lambda st, a=a2: check(lib.dsg_gn_coef(*a, st), "gn_coef"))
+        return coef
+
+    def _fusable(self, hw, cin, cin1, cout) -> bool:
+        eng = self.eng
+        if not (self.fuse_gn and eng.fuse_gn and eng.conv_impl != 1):
+            return False
+        if eng.fuse_gn == 1 and cout % 256 != 0:
+            return False
+        return bool(self.lib.dsg_conv_gn_fusable(0, hw[0], hw[1], cin, cin1, cout))
+
     def _conv(self, mode, x, hw, cin, cout, wname, bname, out, temb_off=None, residual=None, sc1=None, csc1=0,
-              sc2=None, csc2=0, count_sc=True, stats=None):
+              sc2=None, csc2=0, count_sc=True, stats=None, x2=None, cin1=0, gn_coef=None):
         eng, lib = self.eng, self.lib
         a = ConvArgs()
         a.mode, a.n, a.h, a.w, a.cin, a.cout = mode, self.b, hw[0], hw[1], cin, cout
@@ -497,6 +533,8 @@ class _Program:
             a.out_stats = stats.data_ptr()   # the epilogue accumulates the next GroupNorm's statistics
         a.block_n = eng.block_n_override if (eng.block_n_override and cout % eng.block_n_override == 0) else 0
         a.impl = eng.conv_impl
+        if gn_coef is not None:   # fused GroupNorm + SiLU (+ concat) on the input: x / x2 are the RAW tensors
+            a.x2, a.cin1, a.gn_coef = _p(x2), (cin1 or cin), gn_coef.data_ptr()
         self.keep.append(a)
         ref = C.byref(a)
         # reference op count: an identity shortcut panel stands for a residual ADD, not for GEMM work
@@ -508,19 +546,32 @@ class _Program:
 
     def _resnet(self, r, x1, x2, hw, out):
         c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
-        act = self._tmp("act", hw, c1 + c2)
-        st1, st2 = self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
         hbuf = self._tmp("h", hw, co)
         h_stats = self._stats(co)   # the "h" buffer is shared between blocks, its statistics are not
-        self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"],
-                   stats=h_stats)
-        act2 = self._tmp("act", hw, co)
-        self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2, st1=h_stats)
-        if r["has_sc"] or r["id_sc"]:
-            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2,
-                       count_sc=r["has_sc"])
+        act = act2 = None
+        if self._fusable(hw, c1 + c2, c1, co):
+            coef = self._gn_coef(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b")
+            st1 = st2 = None
+            self._conv(0, x1, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"],
+                       stats=h_stats, x2=x2, cin1=c1, gn_coef=coef)
         else:
-            self._conv(0, act2, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, residual=x1)
+            act = self._tmp("act", hw, c1 + c2)
+            st1, st2 = self._gn(x1, c1, x2, c2, hw, f"{pre}.norm1.g", f"{pre}.norm1.b", 1, act)
+            self._conv(0, act, hw, c1 + c2, co, f"{pre}.conv1", f"{pre}.conv1.b", hbuf, temb_off=r["temb_off"],
+                       stats=h_stats)
+        kw = {}
+        if self._fusable(hw, co, co, co):
+            kw = dict(gn_coef=self._gn_coef(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", st1=h_stats))
+            src = hbuf
+        else:
+            act2 = self._tmp("act", hw, co)
+            self._gn(hbuf, co, None, 0, hw, f"{pre}.norm2.g", f"{pre}.norm2.b", 1, act2, st1=h_stats)
+            src = act2
+        if r["has_sc"] or r["id_sc"]:
+            self._conv(0, src, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, sc1=x1, csc1=c1, sc2=x2, csc2=c2,
+                       count_sc=r["has_sc"], **kw)
+        else:
+            self._conv(0, src, hw, co, co, f"{pre}.conv2", f"{pre}.conv2.b", out, residual=x1, **kw)
         return {"kind": "resnet", "r": r, "x1": x1, "x2": x2, "hw": hw, "out": out, "a1": act, "h": hbuf,
                 "h_stats": h_stats, "a2": act2, "st1": st1, "st2": st2}
 
@@ -630,19 +681,27 @@ class _Program:
                 self._record({"kind": "up", "prefix": pre, "x": x, "hw": hw, "out": out, "ch": blk["ch"]})
                 x, hw = out, nhw
         assert not skips
-        act = self._tmp("act", hw, c0)
-        st_out, _ = self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
-        self._record({"kind": "out", "x": x, "hw": hw, "act": act, "st1": st_out, "c0": c0})
         tw = 16 if hw[1] >= 16 else (8 if hw[1] >= 8 else 0)
+        tc_out = bool("conv_out.w16" in W and tw and hw[0] >= 2 * (128 // tw) + 2 and eng.conv_impl != 1)
+        fuse_out = tc_out and self._fusable(hw, c0, c0, 16)
+        coef = act = st_out = None
+        if fuse_out:
+            coef = self._gn_coef(x, c0, None, 0, hw, "norm_out.g", "norm_out.b")
+        else:
+            act = self._tmp("act", hw, c0)
+            st_out, _ = self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
+        self._record({"kind": "out", "x": x, "hw": hw, "act": act, "st1": st_out, "c0": c0})
         meta = {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2), "flops": 2 * b * hw[0] * hw[1] * self.cout * 9 * c0}
-        if "conv_out.w16" in W and tw and hw[0] >= 2 * (128 // tw) + 2 and eng.conv_impl != 1:
+        if tc_out:
             # tcgen05 path: the halo-reuse igemm with BLOCK_N = 16 and an NCHW fp32 epilogue
             a = ConvArgs()
             a.mode, a.n, a.h, a.w, a.cin, a.cout = 0, b, hw[0], hw[1], c0, 16
-            a.x = act.data_ptr()
+            a.x = (x if fuse_out else act).data_ptr()
             a.wpacked = W["conv_out.w16"].data_ptr()
             a.bias = W["conv_out.b16"].data_ptr()
             a.cout_real = self.cout
+            if fuse_out:
+                a.cin1, a.gn_coef = c0, coef.data_ptr()
             self.keep.append(a)
 
             def run_conv_out(st, a=a):

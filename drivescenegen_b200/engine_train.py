@@ -30,6 +30,7 @@ class TrainProgram(_Program):
     def __init__(self, eng: UNetEngine, batch: int, h: int, w: int, grad_slices: Dict[str, torch.Tensor]):
         """grad_slices: parameter name (upstream state-dict key) -> fp32 view that receives its gradient."""
         self.grads = grad_slices
+        self.fuse_gn = False   # the backward needs every normalised tensor (wgrad operand): no in-conv GroupNorm
         self.records: List[dict] = []
         self.bwd_ops: List[Callable[[int], None]] = []
         self.bwd_info: List[Tuple[str, dict]] = []

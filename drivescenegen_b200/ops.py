@@ -138,13 +138,29 @@ def pack_conv_weight(mode: int, w, w_sc=None):
     return out
 
 
+def gn_coef(stats1, stats2, gamma, beta, groups: int, eps: float, hw: int):
+    """coefficients of the fused (in-conv) GroupNorm+SiLU: fp32 [n, c1+c2, 2] = (a/2, b/2)."""
+    _cuda(stats1, stats2, gamma, beta)
+    lib = _lib.load()
+    n, c1 = stats1.shape[0], stats1.shape[1]
+    c2 = 0 if stats2 is None else stats2.shape[1]
+    coef = torch.empty((n, c1 + c2, 2), dtype=torch.float32, device=stats1.device)
+    check(lib.dsg_gn_coef(c1, stats1.data_ptr(), c2, _p(stats2), gamma.data_ptr(), beta.data_ptr(), eps, coef.data_ptr(),
+                          n, hw, groups, _st(stats1)), "gn_coef")
+    return coef
+
+
 def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int = 0, residual=None, sc1=None, sc2=None,
-         block_n: int = 0, impl: int = 0, out_stats=None):
+         block_n: int = 0, impl: int = 0, out_stats=None, x2=None, gn_coef=None):
     """x fp16 NHWC [n,h,w,cin]; returns fp16 NHWC [n,oh,ow,cout] (see dsg_conv in include/dsg_b200.h).
-    out_stats: optional zeroed int64 [n,cout,2] tensor that receives the output's GroupNorm totals."""
-    _cuda(x, wpacked, bias, temb, residual, sc1, sc2)
+    out_stats: optional zeroed int64 [n,cout,2] tensor that receives the output's GroupNorm totals.
+    gn_coef (+ optional x2): fused GroupNorm+SiLU of the raw input cat(x, x2)."""
+    _cuda(x, wpacked, bias, temb, residual, sc1, sc2, x2, gn_coef)
     lib = _lib.load()
     n, h, w, cin = x.shape
+    cin1 = cin
+    if x2 is not None:
+        cin = cin + x2.shape[3]
     oh, ow = (h // 2, w // 2) if mode in (1, 4) else ((h * 2, w * 2) if mode == 2 else (h, w))
     out = torch.empty((n, oh, ow, cout), dtype=torch.float16, device=x.device)
     a = ConvArgs()
@@ -160,6 +176,7 @@ def conv(mode: int, x, wpacked, cout: int, bias=None, temb=None, temb_off: int =
     a.out = out.data_ptr()
     a.block_n, a.impl = block_n, impl
     a.out_stats = _p(out_stats)
+    a.x2, a.cin1, a.gn_coef = _p(x2), cin1, _p(gn_coef)
     check(lib.dsg_conv(C.byref(a), _st(x)), "dsg_conv")
     return out
 

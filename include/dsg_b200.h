@@ -127,8 +127,21 @@ typedef struct dsg_conv_args {
    * The tcgen05 kernels store the total of channels (2k, 2k+1) in channel 2k's slot and leave 2k+1's untouched:
    * valid for dsg_gn_apply whenever the group size and c1 are even (it only sums whole groups). */
   void* out_stats;
+  /* optional fused GroupNorm + SiLU of the INPUT (modes 0 only, halo-reuse kernels — check dsg_conv_gn_fusable):
+   * when gn_coef is non-NULL, x (and x2) hold the RAW tensor(s) the GroupNorm reads — x has cin1 channels, x2 (may
+   * be NULL, then cin1 = cin) the remaining cin - cin1, i.e. the up-block torch.cat is fused too — and the conv input
+   * is SiLU(GroupNorm(cat(x, x2))) formed in shared memory from gn_coef = float[n][cin][2] (dsg_gn_coef). */
+  const void* x2;
+  int32_t cin1;
+  const float* gn_coef;
 } dsg_conv_args;
 int dsg_conv(const dsg_conv_args* args, void* stream);
+/* 1 if dsg_conv can run this shape with gn_coef (fused GroupNorm + SiLU input), else 0 */
+int dsg_conv_gn_fusable(int32_t mode, int32_t h, int32_t w, int32_t cin, int32_t cin1, int32_t cout);
+/* Per-(sample, channel) GroupNorm coefficients for the fused form: coef[n][c] = { a / 2, b / 2 } with
+ * GroupNorm(x) = a x + b (a = gamma * rstd, b = beta - mean * a), from the same statistics dsg_gn_apply takes. */
+int dsg_gn_coef(int32_t c1, const void* stats1, int32_t c2, const void* stats2, const float* gamma, const float* beta,
+                float eps, float* coef, int32_t n, int64_t hw, int32_t groups, void* stream);
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */
 int64_t dsg_packed_k(int32_t mode, int32_t cin, int32_t csc);
 int64_t dsg_packed_rows(int32_t mode, int32_t cout);
