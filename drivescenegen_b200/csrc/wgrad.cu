@@ -236,34 +236,49 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
 // fold table of the upsample conv: 3x3 tap (ky, kx) collects sub-pixel taps (a, b, i(a, ky), j(b, kx))
 __device__ __forceinline__ int up_tap_i(int a, int ky) { return a == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0); }
 
-// ws [splits][co][ktaps][ci] -> out fp32 [co_count][ci_total][KK] (OIHW), rows co_begin.., columns ci_off..ci_off+ci
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int co, int ktaps,
-                                                           int ci, int fold_up, int co_begin, int co_count,
-                                                           int ci_total, int ci_off, const float* __restrict__ inv_scale,
-                                                           float* __restrict__ out, int accumulate) {
+// ws [splits][co][ktaps][ci] -> out fp32 [co_count][ci_total][KK] (OIHW), rows co_begin.., columns ci_off..ci_off+ci.
+// One block per (output channel, 64 input channels): phase 1 reads the workspace coalesced along ci and sums the splits in
+// a fixed order into a [KK][64] shared tile; phase 2 writes the tile transposed, i.e. 64 * KK consecutive floats of the
+// OIHW gradient (a thread-per-element mapping made one of the two sides a 36-byte-stride scatter).
+constexpr int WR_CI = 64;
+__global__ void __launch_bounds__(WR_CI * 9) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int co,
+                                                                 int ktaps, int ci, int fold_up, int co_begin,
+                                                                 int co_count, int ci_total, int ci_off,
+                                                                 const float* __restrict__ inv_scale,
+                                                                 float* __restrict__ out, int accumulate) {
   const int KK = fold_up ? 9 : ktaps;
-  const int64_t total = (int64_t)co_count * KK * ci;
+  __shared__ float tile[9][WR_CI + 1];
+  const int o = blockIdx.y, c0 = blockIdx.x * WR_CI;
+  const int t = threadIdx.x;
   pdl_sync();
   const float s = inv_scale ? *inv_scale : 1.0f;
   const int64_t split_stride = (int64_t)co * ktaps * ci;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ci);
-    const int kk = (int)((i / ci) % KK);
-    const int o = (int)(i / ((int64_t)ci * KK));
-    const float* base = ws + ((int64_t)(co_begin + o) * ktaps) * ci + c;
+  if (t < KK * WR_CI) {
+    const int kk = t / WR_CI, c = t % WR_CI;
     float acc = 0.f;
-    if (fold_up) {
-      const int ky = kk / 3, kx = kk % 3;
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) {
-          const int kt = (a * 2 + b) * 4 + up_tap_i(a, ky) * 2 + up_tap_i(b, kx);
-          for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kt * ci];
-        }
-    } else {
-      for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kk * ci];
+    if (c0 + c < ci) {
+      const float* base = ws + ((int64_t)(co_begin + o) * ktaps) * ci + c0 + c;
+      if (fold_up) {
+        const int ky = kk / 3, kx = kk % 3;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int kt = (a * 2 + b) * 4 + up_tap_i(a, ky) * 2 + up_tap_i(b, kx);
+            for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kt * ci];
+          }
+      } else {
+        for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kk * ci];
+      }
     }
-    float* op = out + ((int64_t)o * ci_total + ci_off + c) * KK + kk;
-    *op = accumulate ? *op + acc * s : acc * s;
+    tile[kk][c] = acc * s;
+  }
+  __syncthreads();
+  if (t < KK * WR_CI) {
+    const int c = t / KK, kk = t % KK;
+    if (c0 + c < ci) {
+      float* op = out + ((int64_t)o * ci_total + ci_off + c0 + c) * KK + kk;
+      const float v = tile[kk][c];
+      *op = accumulate ? *op + v : v;
+    }
   }
 }
 
@@ -511,10 +526,9 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
   }
   launch_k(wgrad_kernel, dim3((unsigned)splits, (unsigned)items), dim3(WG_THREADS), smem_bytes, st, maps, p);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/tcgen05");
-  int64_t blocks = ceil_div64(out_elems, 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(wgrad_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const float*)p.ws, splits, a->cout, p.ktaps,
-           a->cin, a->mode == 2 ? 1 : 0, 0, a->cout, a->ci_total, a->ci_off, a->inv_scale, a->grad, a->accumulate);
+  launch_k(wgrad_reduce_kernel, dim3((unsigned)ceil_div(a->cin, WR_CI), (unsigned)a->cout), dim3(WR_CI * KK), 0, st,
+           (const float*)p.ws, splits, a->cout, p.ktaps, a->cin, a->mode == 2 ? 1 : 0, 0, a->cout, a->ci_total, a->ci_off,
+           a->inv_scale, a->grad, a->accumulate);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/reduce");
   return DSG_OK;
 }
