@@ -7,8 +7,9 @@ One "step" = one DDPM denoising step (U-Net forward + scheduler.step) over a bat
 samples with random-init weights of the reference architecture (DriveSceneGen/scripts/train.py:39-57).
   value     sample-steps/s (= B*K/time), inputs resident in HBM, CUDA events, max over ranks; N>1 = N independent
             replicas (sampling never communicates: SURVEY.md §8e), weak scaling.
-  e2e       same metric through DenoiseSession.step_from_host: every step copies that step's variance noise from
-            pinned host memory to the device and reads the new sample back to pinned host memory.
+  e2e       same metric through DenoiseSession.run_from_host: every step copies that step's variance noise from
+            pinned host memory to the device and reads the new sample back to pinned host memory; the copies run
+            on their own streams beside the next step's compute (serial copy->step->copy->sync time also reported).
   roofline  the tcgen05 implicit-GEMM conv kernel: algorithmic conv/linear FLOPs of one step (reference op count)
             / summed CUDA-event duration of those launches in an eager, per-launch-timed replay of the same step.
   cpu_baseline / --impl reference: the CPU oracle (plain PyTorch fp32 restatement of the reference path) on this
@@ -399,6 +400,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # ------------------------------------------------------------------ end-to-end (host buffers in, host buffer out)
+    # serial form: copy in -> step -> copy out -> host sync, every step
     sess.x.copy_(x0)
     for i in range(3):
         sess.step_from_host(ts[i], noise_host[i % 4], out_host)
@@ -407,7 +409,20 @@ def main():
     for i in range(K):
         sess.step_from_host(ts[(3 + i) % len(ts)], noise_host[i % 4], out_host)
     barrier()
+    e2e_serial_s = time.perf_counter() - t0
+    # pipelined form (the one the pipeline uses with host-side noise): the same bytes cross PCIe every step and
+    # every step's result is read on the host, with the copies on their own streams beside the next step's compute
+    out_hosts = [out_host, torch.empty(shape).pin_memory()]
+    seen = []
+    sess.x.copy_(x0)
+    sess.run_from_host([ts[i] for i in range(3)], noise_host, out_hosts)
+    barrier()
+    t0 = time.perf_counter()
+    sess.run_from_host([ts[(3 + i) % len(ts)] for i in range(K)], noise_host, out_hosts,
+                       on_result=lambda i, o: seen.append(float(o[0, 0, 0, 0])))
+    barrier()
     e2e_s = time.perf_counter() - t0
+    assert len(seen) == K
 
     if world > 1:
         import torch.distributed as dist
@@ -478,7 +493,9 @@ def main():
             "batch_steps_per_s": world * K / (ms * 1e-3), "unet_fwd_ms_eager_sum": total_ms,
             "clocks": clocks,
             "e2e": {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n_bytes,
-                    "d2h_bytes_per_step": n_bytes, "ms_per_step": 1000.0 * e2e_s / K},
+                    "d2h_bytes_per_step": n_bytes, "ms_per_step": 1000.0 * e2e_s / K,
+                    "how": "DenoiseSession.run_from_host: pinned host noise in, host result out every step, copies "
+                           "on side streams", "serial_ms_per_step": 1000.0 * e2e_serial_s / K},
             "gpu_launches": K * sess.launches_per_step,
             "roofline": roofline, "breakdown": breakdown, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

@@ -111,6 +111,12 @@ class ShardedDataLoader:
 
     def _move(self, b):
         if torch.is_tensor(b):
+            if self.device.type == "cuda":
+                from . import raster
+                if raster.is_raster_batch(b):
+                    # RasterDataset batches cross PCIe as bytes and are normalised on the device (dsg_image_to_sample)
+                    src = b if b.is_cuda or b.is_pinned() else b.pin_memory()
+                    return raster.image_to_sample(src.to(self.device, non_blocking=True), channels=min(3, b.shape[3]))
             return b.to(self.device, non_blocking=True)
         if isinstance(b, (list, tuple)):
             return type(b)(self._move(x) for x in b)

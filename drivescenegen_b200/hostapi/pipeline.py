@@ -106,6 +106,77 @@ class DenoiseSession:
         torch.cuda.current_stream(self.dev).synchronize()
         return out_host
 
+    def _pipe_state(self):
+        if getattr(self, "_pipe", None) is None:
+            ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+            self._pipe = {"h2d": torch.cuda.Stream(device=self.dev), "d2h": torch.cuda.Stream(device=self.dev),
+                          "z": [torch.zeros_like(self.z), torch.zeros_like(self.z)],
+                          "x": [torch.zeros_like(self.x), torch.zeros_like(self.x)],
+                          "z_in": ev(), "z_free": ev(), "x_ready": ev(), "x_out": ev()}
+        return self._pipe
+
+    def run_from_host(self, timesteps, noise_host, out_host, on_result=None):
+        """End-to-end loop with the copies taken off the critical path.
+
+        Step ``i`` takes its variance noise from the pinned host tensor ``noise_host[i % len(noise_host)]`` and lands its
+        new sample in the pinned host tensor ``out_host[i % len(out_host)]`` (``len(out_host) >= 2``).  The host->device
+        copy of step ``i+1`` and the device->host copy of step ``i-1`` run on their own streams while the graph of step
+        ``i`` computes (a step depends on the previous step's sample only on the device); the host waits for result
+        ``i-1`` after it has queued step ``i`` and then calls ``on_result(i-1, tensor)``.  Every step's input still
+        crosses PCIe and every step's result is still read on the host before the call returns.
+        """
+        if len(out_host) < 2:
+            raise ValueError("run_from_host needs at least two host output buffers")
+        ps = self._pipe_state()
+        main = torch.cuda.current_stream(self.dev)
+        n = len(timesteps)
+        nz = len(noise_host)
+        started = [False, False]      # has stage slot s been used in this call (events valid)?
+
+        def h2d(i):
+            s = i % 2
+            with torch.cuda.stream(ps["h2d"]):
+                if started[s]:
+                    ps["h2d"].wait_event(ps["z_free"][s])
+                else:
+                    ps["h2d"].wait_stream(main)
+                ps["z"][s].copy_(noise_host[i % nz], non_blocking=True)
+                ps["z_in"][s].record(ps["h2d"])
+
+        outs = [False, False]
+        if n:
+            h2d(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                h2d(i + 1)
+            main.wait_event(ps["z_in"][s])
+            self.z.copy_(ps["z"][s])
+            ps["z_free"][s].record(main)
+            started[s] = True
+            self.set_step(int(timesteps[i]))
+            self.graph.replay()
+            if outs[s]:
+                main.wait_event(ps["x_out"][s])      # the copy out of this stage slot two steps ago has finished
+            ps["x"][s].copy_(self.x)
+            ps["x_ready"][s].record(main)
+            with torch.cuda.stream(ps["d2h"]):
+                ps["d2h"].wait_event(ps["x_ready"][s])
+                out_host[i % len(out_host)].copy_(ps["x"][s], non_blocking=True)
+                ps["x_out"][s].record(ps["d2h"])
+            outs[s] = True
+            if i >= 1:
+                ps["x_out"][(i - 1) % 2].synchronize()
+                if on_result is not None:
+                    on_result(i - 1, out_host[(i - 1) % len(out_host)])
+        if n:
+            ps["x_out"][(n - 1) % 2].synchronize()
+            if on_result is not None:
+                on_result(n - 1, out_host[(n - 1) % len(out_host)])
+        main.wait_stream(ps["h2d"])
+        main.wait_stream(ps["d2h"])
+        return out_host[(n - 1) % len(out_host)] if n else None
+
 
 class DDPMPipeline:
     config_name = "model_index.json"

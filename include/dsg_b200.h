@@ -59,6 +59,32 @@ int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const f
 int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, int32_t n, int32_t c, int32_t h,
                         int32_t w, void* stream);
 
+/* ---------------------------------------------------------------- raster images either side of the path ---- */
+/* Input side — replaces the per-item arithmetic of Image_Dataset.__getitem__
+ * (DriveSceneGen/utils/datasets/dataset.py:20-23,44-47): ToTensor (x / 255) then Normalize([0.5], [0.5])
+ * ((x - 0.5) / 0.5), each fp32 operation rounded separately like torchvision.  img: uint8 [n][h][w][c_img] (what PIL
+ * decodes), out: float [n][c_out][h][w] = channels 0..c_out-1.  The Resize in the reference transform is the identity
+ * when the stored raster already has the model's size; other sizes are the caller's business. */
+int dsg_image_to_sample(const uint8_t* img, float* out, int32_t n, int32_t h, int32_t w, int32_t c_img, int32_t c_out,
+                        void* stream);
+/* Vectoriser front end — replaces get_gray_image
+ * (DriveSceneGen/vectorization/utils/image_utils.py:13-42) for a batch of rasters that are still on the device.
+ *   img   uint8 [n][h][w][c], c = 3 or 4 (channel 0 = dx, 1 = dy, 2 = speed)
+ *   hist  uint32 [n][3][256] out: np.histogram(channel / 255.0, bins=256, range=(0, 1)) (zeroed by the call)
+ *   peaks int32 [n][3] out: np.argmax of each histogram (first maximum); the peak value is peaks / 256.0
+ *   mask  uint8 [n][h][w] out: 0 where |dx/255 - peak_dx/256| <= thresh and |dy/255 - peak_dy/256| <= thresh (float64
+ *         comparisons like combine_dx_dy, image_utils.py:6-10), else 255
+ *   gray3 uint8 [n][h][w][3] out, may be NULL: the mask repeated over three channels (what Image.fromarray receives) */
+int dsg_gray_mask(const uint8_t* img, uint32_t* hist, int32_t* peaks, uint8_t* mask, uint8_t* gray3, int32_t n,
+                  int32_t h, int32_t w, int32_t c, double thresh, void* stream);
+/* Agent blobs — replaces the per-pixel head of extract_agents
+ * (DriveSceneGen/vectorization/direct/extract_vehicles.py:136-148): img = (x * 255).astype(uint8) (truncation, x in
+ * [0, 1]), cv2.cvtColor of three equal channels (identity), cv2.threshold(gray, thresh, 255, THRESH_BINARY).
+ * plane: n float planes of hw values (the speed channel), plane i at plane + i * plane_stride; out uint8 [n][hw].
+ * cv2.findContours / minAreaRect stay on the host. */
+int dsg_agent_threshold(const float* plane, int64_t plane_stride, uint8_t* out, int32_t n, int64_t hw, int32_t thresh,
+                        void* stream);
+
 /* ---------------------------------------------------------------- U-Net building blocks ------------------- */
 /* Timesteps + TimestepEmbedding + all per-ResnetBlock time_emb_proj in two launches.
  *   t: float[batch] (timestep values), freqs: float[half] (exp table, host-computed like upstream),

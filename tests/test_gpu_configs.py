@@ -54,3 +54,39 @@ def test_ddim_pipeline_50_steps_512_properties():
     # which can flip a few fp16 roundings: agreement at fp16 resolution, not bit-identity
     assert (e2[:1] - e1).abs().max().item() <= 5e-3 * e1.abs().max().item()
     assert ((e2[:1] - e1).norm() / e1.norm()).item() < 1e-3
+
+
+def test_run_from_host_pipelined_equals_serial_loop():
+    """DenoiseSession.run_from_host (copies on side streams) gives bit-identical samples to the serial
+    copy-in / step / copy-out loop, and hands every step's result to the host exactly once, in order."""
+    from drivescenegen_b200.hostapi import DDPMScheduler, DenoiseSession, UNet2DModel
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    model = UNet2DModel(sample_size=64, block_out_channels=(64, 128), down_block_types=("DownBlock2D",) * 2,
+                        up_block_types=("UpBlock2D",) * 2).to(dev).eval()
+    sched = DDPMScheduler()
+    sched.set_timesteps(1000)
+    shape = (2, 3, 64, 64)
+    sess = DenoiseSession(model, sched, shape)
+    gen = torch.Generator().manual_seed(5)
+    x0 = torch.randn(shape, generator=gen)
+    noise = [torch.randn(shape, generator=gen).pin_memory() for _ in range(3)]
+    ts = [int(t) for t in sched.timesteps[:7]]
+
+    out = torch.empty(shape).pin_memory()
+    serial = []
+    sess.x.copy_(x0)
+    for i, t in enumerate(ts):
+        serial.append(sess.step_from_host(t, noise[i % 3], out).clone())
+
+    outs = [torch.empty(shape).pin_memory() for _ in range(2)]
+    got = []
+    for n in (len(ts), 1, 0):      # full run, a single step, an empty run
+        got.clear()
+        sess.x.copy_(x0)
+        sess.run_from_host(ts[:n], noise, outs, on_result=lambda i, o: got.append((i, o.clone())))
+        assert [i for i, _ in got] == list(range(n))
+        for (i, o), ref in zip(got, serial):
+            assert torch.equal(o, ref), f"step {i} differs"
+    with pytest.raises(ValueError):
+        sess.run_from_host(ts, noise, outs[:1])

@@ -41,13 +41,17 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--sizes", default="64,128,256,512")
     ap.add_argument("--batches", default="1,8,16")
+    ap.add_argument("--raster", action="store_true", help="also sweep the byte-image kernels (raster.cu)")
+    ap.add_argument("--raster-only", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peaks()
     flush = torch.zeros(64 << 20, device=dev)
     rows = []
     chans = (64, 128, 256, 512)
-    for size in [int(s) for s in args.sizes.split(",")]:
+    if args.raster_only:
+        args.raster = True
+    for size in ([] if args.raster_only else [int(s) for s in args.sizes.split(",")]):
         for b in [int(s) for s in args.batches.split(",")]:
             if size == 512 and b > 8:
                 continue
@@ -74,6 +78,33 @@ def main():
                 rows.append({"op": "attention_64h_d8", "px": size, "batch": b, "tokens": tokens, "ms": ms,
                              "Gexp_s": b * 64 * tokens * tokens / ms / 1e6,
                              "TFLOPs": 4.0 * b * tokens * tokens * 512 / ms / 1e9})
+    if args.raster:
+        from drivescenegen_b200.hostapi import raster
+        import numpy as np
+        rng = np.random.default_rng(0)
+        for size in [int(s) for s in args.sizes.split(",")]:
+            for b in (16, 256):
+                if size == 512 and b > 64:
+                    b = 64
+                img = rng.integers(0, 256, (b, size, size, 3), dtype=np.uint8)
+                bg = rng.random((b, size, size)) < 0.9          # BEV rasters: one dominant background value
+                img[..., 0] = np.where(bg, 127, img[..., 0])
+                img[..., 1] = np.where(bg, 128, img[..., 1])
+                img = torch.from_numpy(img).to(dev)
+                px = b * size * size
+                out = torch.empty((b, 3, size, size), device=dev)
+                ms = timed(lambda: raster.image_to_sample(img, out=out), flush=flush)
+                nb = px * (3 + 12)
+                rows.append({"op": "image_to_sample", "px": size, "batch": b, "ms": ms, "GBs": nb / ms / 1e6,
+                             "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"]})
+                ms = timed(lambda: raster.gray_masks(img), flush=flush)
+                nb = px * (3 + 3 + 1)     # histogram pass + mask pass read the image, mask pass writes 1 B/px
+                rows.append({"op": "gray_mask(hist+mask)", "px": size, "batch": b, "ms": ms, "GBs": nb / ms / 1e6,
+                             "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"]})
+                ms = timed(lambda: raster.agent_threshold(out), flush=flush)
+                nb = px * (4 + 1)
+                rows.append({"op": "agent_threshold", "px": size, "batch": b, "ms": ms, "GBs": nb / ms / 1e6,
+                             "frac_hbm": nb / ms / 1e6 / pk["hbm_gbs"]})
     doc = {"peaks": pk, "note": "min of 5 CUDA-event timings, L2 flushed between iterations; conv fraction is of the "
                                 "measured BURST bf16 peak (kernel timed alone)", "rows": rows}
     txt = json.dumps(doc, indent=1)
