@@ -78,6 +78,205 @@ __global__ void __launch_bounds__(CS_THREADS, 2) conv_in_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------ conv_in on the tensor cores, statistics fused
+// K = cin * 9 <= 32 and N = 64: far too thin for a tcgen05 tile (the K axis would be padded 20x), but on CUDA cores the
+// layer is FP32-FMA bound at ~3x its HBM time.  This form uses warp-level mma.sync m16n8k16 (fp16 operands, fp32
+// accumulate — the numerics of every other conv of the U-Net): a warp owns one image row of the block's 8-row strip and
+// walks it 16 pixels at a time.  A fragments are gathered from a (8 + 2) x (W + 2) fp16 window staged in shared memory
+// (one 16-bit load per element; the k -> (ci, ky, kx) offsets are per-thread constants), all B fragments (the whole
+// 32 x 64 weight matrix) live in 32 registers per thread, the fp16 NHWC result goes straight to global memory, and the
+// per-channel sum / sum of squares of the next GroupNorm ride along in registers (one int64 atomic per (sample,
+// channel, statistic) per strip) — the separate statistics pass over conv_in's output is gone.
+constexpr int CM_ROWS = 8;    // rows per strip = warps per block
+constexpr int CM_NT = 8;      // n-tiles of 8 output channels (cout = 64)
+constexpr int CM_OPITCH = 144; // bytes per pixel row of the per-warp output staging tile
+
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16_16(uint32_t addr) {   // the same element 8 pixels to the right
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+16];" : "=h"(v) : "r"(addr));
+  return v;
+}
+
+// FULL: the row length is a multiple of 16 (no partial tile, no bounds checks in the pixel loop)
+template <bool FULL>
+__global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ b,
+                                                                      __half* __restrict__ out,
+                                                                      long long* __restrict__ stats, int n, int cin,
+                                                                      int h, int wd) {
+  extern __shared__ __align__(16) unsigned char cm_smem[];
+  const int P = (wd + 2 + 15) & ~15;          // window pitch (halves): column 0 = image column -1; the tail is zero
+  const int plane = (CM_ROWS + 2) * P;
+  // [cin + 2][CM_ROWS + 2][P]: plane `cin` is all ones, plane `cin + 1` all zeros.  K slots cin * 9 and cin * 9 + 1
+  // gather ones and multiply the bias (split into an fp16 head and an fp16 remainder: exact to ~2^-22), the remaining
+  // padded slots gather zeros — no bias registers, no predicates in the pixel loop.
+  __half* s_in = reinterpret_cast<__half*>(cm_smem);
+  float* s_stat = reinterpret_cast<float*>(cm_smem + (size_t)(cin + 2) * plane * 2);  // [8][64][2]
+  // per-warp staging of one 16-pixel x 64-channel output tile (pitch 144 B: conflict-free both ways): the accumulator
+  // fragments hold 4-byte pieces of 8 different pixels, the tile itself is 2 KB of contiguous NHWC memory
+  unsigned char* s_out = reinterpret_cast<unsigned char*>(s_stat + CM_ROWS * 64 * 2) + (threadIdx.x >> 5) * (16 * CM_OPITCH);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int K = cin * 9;
+  for (int i = threadIdx.x; i < plane; i += CM_ROWS * 32) {
+    s_in[cin * plane + i] = __float2half_rn(1.f);
+    s_in[(cin + 1) * plane + i] = __float2half_rn(0.f);
+  }
+  pdl_sync();
+  // B fragments: b0 = W[k = 16s + 2t, 2t + 1][n = 8j + g], b1 = W[k + 8, k + 9][n]; W[k][n] = w[n][k] (OIHW, k < K)
+  uint32_t bf[2][CM_NT][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < CM_NT; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k0 = ks * 16 + hh * 8 + 2 * t, nn = j * 8 + g;
+        float wv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = k0 + u;
+          const float bh = __half2float(__float2half_rn(b[nn]));
+          wv[u] = k < K ? w[nn * K + k] : (k == K ? bh : (k == K + 1 ? b[nn] - bh : 0.f));
+        }
+        const __half2 hv = __floats2half2_rn(wv[0], wv[1]);
+        bf[ks][j][hh] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+  // A gather: element i of the thread's fragment list is k = (i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2t + (i & 1);
+  // byte offset of that tap inside the window, relative to (row of the warp, pixel column)
+  uint32_t aoff[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = (i >> 2) * 16 + ((i >> 1) & 1) * 8 + 2 * t + (i & 1);
+    int ci = k < K + 2 ? cin : cin + 1, ky = 0, kx = 0;   // bias slots -> ones plane, the rest -> zeros plane
+    if (k < K) { ci = k / 9; ky = (k - ci * 9) / 3; kx = k - ci * 9 - ky * 3; }
+    aoff[i] = (uint32_t)(ci * plane + ky * P + kx) * 2u;
+  }
+
+  const int strips = (h + CM_ROWS - 1) / CM_ROWS;
+  const int64_t items = (int64_t)n * strips;
+  const int64_t hw = (int64_t)h * wd;
+  const uint32_t row_u32 = smem_u32(s_in) + (uint32_t)(warp * P + g) * 2u;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int nn = (int)(item / strips), y0 = (int)(item % strips) * CM_ROWS;
+    __syncthreads();   // the previous strip's window and statistics scratch are no longer in use
+    // window rows are spread over the warps; all loads of a row chunk (8 x 32 columns) are issued before the first
+    // shared-memory store — a load-store-load-store loop would put one DRAM round trip per 32 columns on the critical path
+    for (int rr = warp; rr < cin * (CM_ROWS + 2); rr += CM_ROWS) {
+      const int ci = rr / (CM_ROWS + 2), r = rr - ci * (CM_ROWS + 2);
+      const int yy = y0 - 1 + r;
+      const bool row_ok = yy >= 0 && yy < h;
+      const float* xp = x + ((int64_t)nn * cin + ci) * hw + (int64_t)yy * wd;
+      __half* sp = s_in + ci * plane + r * P;
+      for (int c0 = 0; c0 < P; c0 += 8 * 32) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int xx = c0 + u * 32 + lane - 1;
+          v[u] = row_ok && xx >= 0 && xx < wd ? __ldg(xp + xx) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c = c0 + u * 32 + lane;
+          if (c < P) sp[c] = __float2half_rn(v[u]);
+        }
+      }
+    }
+    __syncthreads();
+    float ssum[CM_NT][2], ssq[CM_NT][2];
+#pragma unroll
+    for (int j = 0; j < CM_NT; ++j) { ssum[j][0] = ssum[j][1] = 0.f; ssq[j][0] = ssq[j][1] = 0.f; }
+    const int y = y0 + warp;
+    if (y < h) {
+      unsigned char* otile = reinterpret_cast<unsigned char*>(out + (((int64_t)nn * h + y) * wd) * 64) + lane * 16;
+      unsigned char* so_w = s_out + g * CM_OPITCH + t * 4;                    // fragment piece (pixel g, n-tile 0)
+      const unsigned char* so_r = s_out + (lane >> 3) * CM_OPITCH + (lane & 7) * 16;  // 16 B of pixel lane / 8 (+ 4i)
+      uint32_t pa = row_u32;
+      for (int x0 = 0; x0 < wd; x0 += 16, pa += 32, otile += 16 * 128) {
+        // fragment registers: 0 = (pixel g, k lo pair), 1 = (pixel g + 8, k lo), 2 = (g, k hi), 3 = (g + 8, k hi).
+        // The window pitch is padded to 16 columns, so a partial last tile reads zeros / finite values it never stores.
+        uint32_t af[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int i0 = ks * 4 + hh * 2;
+            af[ks][hh * 2] = lds_u16(pa + aoff[i0]) | (lds_u16(pa + aoff[i0 + 1]) << 16);
+            af[ks][hh * 2 + 1] = lds_u16_16(pa + aoff[i0]) | (lds_u16_16(pa + aoff[i0 + 1]) << 16);
+          }
+        const bool va = FULL || x0 + g < wd, vb = FULL || x0 + g + 8 < wd;
+#pragma unroll
+        for (int j = 0; j < CM_NT; ++j) {
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_m16n8k16(d, af[0], bf[0][j][0], bf[0][j][1]);
+          mma_m16n8k16(d, af[1], bf[1][j][0], bf[1][j][1]);
+          *reinterpret_cast<__half2*>(so_w + j * 16) = __floats2half2_rn(d[0], d[1]);
+          *reinterpret_cast<__half2*>(so_w + 8 * CM_OPITCH + j * 16) = __floats2half2_rn(d[2], d[3]);
+          if (FULL) {
+            ssum[j][0] += d[0] + d[2]; ssum[j][1] += d[1] + d[3];
+            ssq[j][0] = fmaf(d[0], d[0], fmaf(d[2], d[2], ssq[j][0]));
+            ssq[j][1] = fmaf(d[1], d[1], fmaf(d[3], d[3], ssq[j][1]));
+          } else {
+            if (va) {
+              ssum[j][0] += d[0]; ssum[j][1] += d[1];
+              ssq[j][0] = fmaf(d[0], d[0], ssq[j][0]); ssq[j][1] = fmaf(d[1], d[1], ssq[j][1]);
+            }
+            if (vb) {
+              ssum[j][0] += d[2]; ssum[j][1] += d[3];
+              ssq[j][0] = fmaf(d[2], d[2], ssq[j][0]); ssq[j][1] = fmaf(d[3], d[3], ssq[j][1]);
+            }
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // 4 x (32 lanes x 16 B) = the tile's 2 KB, in address order
+          if (FULL || x0 + i * 4 + (lane >> 3) < wd)
+            stg_v4(otile + i * 512, *reinterpret_cast<const uint4*>(so_r + i * 4 * CM_OPITCH));
+        }
+        __syncwarp();
+      }
+    }
+    // statistics of the strip: over the 8 pixel lanes of the warp (fixed butterfly), then over the 8 warps (fixed order)
+#pragma unroll
+    for (int j = 0; j < CM_NT; ++j)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float a = ssum[j][u], q = ssq[j][u];
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, off);
+          q += __shfl_xor_sync(0xffffffffu, q, off);
+        }
+        if (g == 0) {
+          s_stat[(warp * 64 + j * 8 + 2 * t + u) * 2] = a;
+          s_stat[(warp * 64 + j * 8 + 2 * t + u) * 2 + 1] = q;
+        }
+      }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
+      float tot = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < CM_ROWS; ++wv) tot += s_stat[(wv * 64 + c) * 2 + k];
+      const long long fx = k ? gn_fix_sq(tot) : gn_fix_sum(tot);
+      atomicAdd(reinterpret_cast<unsigned long long*>(stats + ((int64_t)nn * 64 + c) * 2 + k), (unsigned long long)fx);
+    }
+  }
+}
+
 // warp = 8 adjacent pixels x 4 lanes; each lane owns cin/4 input channels; lanes reduced by shuffle.
 // Weights in smem as [tap][co][cin].
 template <int MAXCO>
@@ -168,6 +367,36 @@ int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, i
            (__half*)out_h16, n, cin, h, wd, cout);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_in");
   return DSG_OK;
+}
+
+int dsg_conv_in_stats(const float* x, const float* w, const float* b, void* out_h16, void* stats, int32_t n,
+                      int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream) {
+  DSG_CHECK_ARG(x && w && b && out_h16 && stats, "dsg_conv_in_stats: null pointer");
+  DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_in_stats: bad shape");
+  if (n == 0) return DSG_OK;
+  const size_t sm = (size_t)(cin + 2) * (CM_ROWS + 2) * ((wd + 2 + 15) & ~15) * 2 + CM_ROWS * 64 * 2 * sizeof(float) +
+                    CM_ROWS * 16 * CM_OPITCH;
+  if (cout == 64 && cin >= 1 && cin * 9 + 2 <= 32 && sm <= 100 * 1024 && (uintptr_t)out_h16 % 16 == 0) {
+    const int64_t items = (int64_t)n * ((h + CM_ROWS - 1) / CM_ROWS);
+    const int64_t blocks = items < 148 * 2 ? items : 148 * 2;  // persistent: weights are loaded once per block
+    if (wd % 16 == 0) {
+      if (sm > 48 * 1024)
+        cudaFuncSetAttribute(conv_in_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      launch_k(conv_in_mma_kernel<true>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, (cudaStream_t)stream, x, w, b,
+               (__half*)out_h16, (long long*)stats, n, cin, h, wd);
+    } else {
+      if (sm > 48 * 1024)
+        cudaFuncSetAttribute(conv_in_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      launch_k(conv_in_mma_kernel<false>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, (cudaStream_t)stream, x, w, b,
+               (__half*)out_h16, (long long*)stats, n, cin, h, wd);
+    }
+    DSG_CUDA_LAUNCH_CHECK("dsg_conv_in_stats");
+    return DSG_OK;
+  }
+  // other widths: the CUDA-core kernel, then one read of its output for the statistics
+  int rc = dsg_conv_in(x, w, b, out_h16, n, cin, h, wd, cout, stream);
+  if (rc != DSG_OK) return rc;
+  return dsg_gn_stats(out_h16, cout, stats, n, (int64_t)h * wd, stream);
 }
 
 int dsg_conv_out(const void* x_h16, const float* w, const float* b, float* out, int32_t n, int32_t cin, int32_t h,

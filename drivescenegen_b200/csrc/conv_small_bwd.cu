@@ -72,16 +72,18 @@ __global__ void __launch_bounds__(256) conv_out_dgrad_weight_kernel(const float*
 }
 
 // grid-stride over image rows; thread = (PAIR of wide channels, x slice); 2 * 9 * NC accumulators per thread.
-// The pixel loop is unrolled four deep with the loads issued first: one 4-byte load per pixel per thread is pure
-// latency otherwise.
+// A thread takes FOUR adjacent pixels per step: their 3 x 3 windows of the narrow tensor overlap, so one (channel, row) of
+// the window costs 6 shared-memory loads for 24 FMA pairs (a pixel at a time it was 3 loads per 3).  The loop always runs
+// the conv_in geometry (narrow at q + tap - 1); the conv_out form (narrow at q - tap + 1) is the same sum with the tap
+// index mirrored, applied when the accumulators are written out.  The reduction scratch reuses the row buffer.
 template <int NC>
 __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* __restrict__ wide,
                                                                  const float* __restrict__ narrow, int n, int h, int w,
                                                                  int wc, int sgn, float* __restrict__ partial) {
-  extern __shared__ float sm[];  // [NC][3][w + 2] rows y-1..y+1 of the narrow tensor, zero padded; then reduction
-  const int ws = w + 2;
+  extern __shared__ float sm[];  // [NC][3][ws] rows y-1..y+1 of the narrow tensor, zero padded; reduction scratch after
+  const int ws = w + 8;          // column x + 1 holds pixel x; columns 0 and w + 1 .. w + 7 are zero
   float* s_rows = sm;
-  float* s_red = sm + NC * 3 * ws;  // [slices][NC * 9][wc] reused after the loop
+  float* s_red = sm;             // [slices][NC * 9][wc], used after the loop
   const int wc2 = wc >> 1;
   const int c_t = threadIdx.x % wc2, slice = threadIdx.x / wc2, nslices = SB_THREADS / wc2;
   float acc[NC][9][2];
@@ -111,31 +113,28 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
     }
     __syncthreads();
     const __half2* wp = reinterpret_cast<const __half2*>(wide + (((int64_t)nn * h + y) * w) * wc) + c_t;
-    for (int x0 = slice; x0 < w; x0 += nslices * U) {
-      __half2 av[U];
+    for (int x0 = slice * U; x0 < w; x0 += nslices * U) {
+      float2 a[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int xx = x0 + u * nslices;
-        av[u] = xx < w ? wp[(int64_t)xx * wc2] : __floats2half2_rn(0.f, 0.f);
-      }
+      for (int u = 0; u < U; ++u)
+        a[u] = x0 + u < w ? __half22float2(wp[(int64_t)(x0 + u) * wc2]) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int xx = x0 + u * nslices;
-        if (xx >= w) continue;
-        const float2 a = __half22float2(av[u]);
+      for (int c = 0; c < NC; ++c)
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
+        for (int ky = 0; ky < 3; ++ky) {
+          // pixels x0 .. x0 + 3 with taps kx = 0..2 read smem columns x0 + u + kx = x0 .. x0 + 5
+          const float* rowp = s_rows + (c * 3 + ky) * ws + x0;
+          float nv[U + 2];
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+          for (int j = 0; j < U + 2; ++j) nv[j] = rowp[j];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              // narrow at q + sgn * (ky - 1, kx - 1); smem column index = x + 1
-              const int ry = 1 + sgn * (ky - 1), cx = xx + 1 + sgn * (kx - 1);
-              const float nv = s_rows[(c * 3 + ry) * ws + cx];
-              acc[c][ky * 3 + kx][0] = fmaf(a.x, nv, acc[c][ky * 3 + kx][0]);
-              acc[c][ky * 3 + kx][1] = fmaf(a.y, nv, acc[c][ky * 3 + kx][1]);
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              acc[c][ky * 3 + kx][0] = fmaf(a[u].x, nv[u + kx], acc[c][ky * 3 + kx][0]);
+              acc[c][ky * 3 + kx][1] = fmaf(a[u].y, nv[u + kx], acc[c][ky * 3 + kx][1]);
             }
-      }
+        }
     }
   }
   __syncthreads();
@@ -143,8 +142,9 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      s_red[(slice * NC * 9 + c * 9 + t) * wc + 2 * c_t] = acc[c][t][0];
-      s_red[(slice * NC * 9 + c * 9 + t) * wc + 2 * c_t + 1] = acc[c][t][1];
+      const int to = sgn > 0 ? t : 8 - t;
+      s_red[(slice * NC * 9 + c * 9 + to) * wc + 2 * c_t] = acc[c][t][0];
+      s_red[(slice * NC * 9 + c * 9 + to) * wc + 2 * c_t + 1] = acc[c][t][1];
     }
   __syncthreads();
   float* o = partial + (int64_t)blockIdx.x * (NC * 9 * wc + NC);
@@ -218,7 +218,8 @@ int dsg_small_wgrad(const void* wide_h16, const float* narrow_nchw, int32_t n, i
   DSG_CHECK_ARG(n >= 0 && h > 0 && w > 0 && parts >= 1, "dsg_small_wgrad: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   const int nslices = SB_THREADS / (wc / 2);
-  const size_t sm = (size_t)(nc * 3 * (w + 2) + nslices * nc * 9 * wc) * sizeof(float);
+  const size_t sm_rows = (size_t)nc * 3 * (w + 8), sm_red = (size_t)nslices * nc * 9 * wc;
+  const size_t sm = (sm_rows > sm_red ? sm_rows : sm_red) * sizeof(float);
   DSG_CHECK_ARG(sm <= 200 * 1024, "dsg_small_wgrad: row too wide for shared memory");
   const int sgn = conv_out_form ? -1 : 1;
 #define DSG_SW_LAUNCH(NCV)                                                                                          \

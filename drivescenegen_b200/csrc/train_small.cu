@@ -13,25 +13,37 @@ __device__ __forceinline__ float silu_grad_exact(float y) {
   return sg * (1.0f + y * (1.0f - sg));
 }
 
-// dx[n][k] = (sum_r dy[n][dy_off + r] * w[r][k]) * (pre ? silu'(pre[n][k]) : 1);  w is [rows][cols] (torch [out][in])
-__global__ void __launch_bounds__(256) lin_dgrad_small_kernel(const float* __restrict__ dy, int ldy, int dy_off,
-                                                              const float* __restrict__ w, int rows, int cols,
-                                                              const float* __restrict__ pre, float* __restrict__ dx,
-                                                              int batch) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// dx[n][k] = (sum_r dy[n][dy_off + r] * w[r][k]) * (pre ? silu'(pre[n][k]) : 1);  w is [rows][cols] (torch [out][in]).
+// One block per (16 columns, sample): 16 row lanes stride over the rows (5824 for the time_emb_proj stack — one thread per
+// output walked them serially), then the lanes are summed in a fixed order (deterministic).
+constexpr int LD_KT = 16, LD_RL = 16;
+__global__ void __launch_bounds__(LD_KT * LD_RL) lin_dgrad_small_kernel(const float* __restrict__ dy, int ldy, int dy_off,
+                                                                        const float* __restrict__ w, int rows, int cols,
+                                                                        const float* __restrict__ pre,
+                                                                        float* __restrict__ dx, int batch) {
+  __shared__ float part[LD_RL][LD_KT + 1];
+  const int kx = threadIdx.x % LD_KT, ry = threadIdx.x / LD_KT;
+  const int k = blockIdx.x * LD_KT + kx;
   const int n = blockIdx.y;
-  if (k >= cols || n >= batch) return;
   const float* d = dy + (int64_t)n * ldy + dy_off;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int r = 0;
-  for (; r + 4 <= rows; r += 4) {
+  if (k < cols) {
+    int r = ry;
+    for (; r + 3 * LD_RL < rows; r += 4 * LD_RL) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = fmaf(d[r + u], w[(int64_t)(r + u) * cols + k], acc[u]);
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(d[r + u * LD_RL], w[(int64_t)(r + u * LD_RL) * cols + k], acc[u]);
+    }
+    for (; r < rows; r += LD_RL) acc[0] = fmaf(d[r], w[(int64_t)r * cols + k], acc[0]);
   }
-  for (; r < rows; ++r) acc[0] = fmaf(d[r], w[(int64_t)r * cols + k], acc[0]);
-  float v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  if (pre) v *= silu_grad_exact(pre[(int64_t)n * cols + k]);
-  dx[(int64_t)n * cols + k] = v;
+  part[ry][kx] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (ry == 0 && k < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < LD_RL; ++i) v += part[i][kx];
+    if (pre) v *= silu_grad_exact(pre[(int64_t)n * cols + k]);
+    dx[(int64_t)n * cols + k] = v;
+  }
 }
 
 // dw[r][k] = s * sum_n dy[n][dy_off + r] * x[n][k];  db[r] = s * sum_n dy[n][dy_off + r]   (x optional-activated)
@@ -162,8 +174,8 @@ int dsg_lin_dgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
                         const float* pre, float* dx, int32_t batch, void* stream) {
   DSG_CHECK_ARG(dy && w && dx && rows > 0 && cols > 0 && batch >= 0 && batch <= 65535, "dsg_lin_dgrad_small: bad args");
   if (batch == 0) return DSG_OK;
-  lin_dgrad_small_kernel<<<dim3(ceil_div(cols, 256), batch), 256, 0, (cudaStream_t)stream>>>(dy, ldy, dy_off, w, rows,
-                                                                                            cols, pre, dx, batch);
+  lin_dgrad_small_kernel<<<dim3(ceil_div(cols, LD_KT), batch), LD_KT * LD_RL, 0, (cudaStream_t)stream>>>(
+      dy, ldy, dy_off, w, rows, cols, pre, dx, batch);
   DSG_CUDA_LAUNCH_CHECK("dsg_lin_dgrad_small");
   return DSG_OK;
 }

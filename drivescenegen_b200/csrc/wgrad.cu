@@ -237,48 +237,84 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
 __device__ __forceinline__ int up_tap_i(int a, int ky) { return a == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0); }
 
 // ws [splits][co][ktaps][ci] -> out fp32 [co_count][ci_total][KK] (OIHW), rows co_begin.., columns ci_off..ci_off+ci.
-// One block per (output channel, 64 input channels): phase 1 reads the workspace coalesced along ci and sums the splits in
-// a fixed order into a [KK][64] shared tile; phase 2 writes the tile transposed, i.e. 64 * KK consecutive floats of the
-// OIHW gradient (a thread-per-element mapping made one of the two sides a 36-byte-stride scatter).
-constexpr int WR_CI = 64;
-__global__ void __launch_bounds__(WR_CI * 9) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int co,
-                                                                 int ktaps, int ci, int fold_up, int co_begin,
-                                                                 int co_count, int ci_total, int ci_off,
-                                                                 const float* __restrict__ inv_scale,
-                                                                 float* __restrict__ out, int accumulate) {
+// One block per (output channel, ci_b input channels): phase 1 walks the KK x ci_b slab coalesced along ci, several
+// elements per thread with the loads of all splits in flight, sums the splits in a fixed order into a shared tile;
+// phase 2 writes the tile transposed, i.e. ci_b * KK consecutive floats of the OIHW gradient.
+constexpr int WR_THREADS = 256, WR_CI_MAX = 256, WR_PITCH = WR_CI_MAX + 1;
+// EPT = elements per thread (KK * ci_b / 256 rounded up), SPU = splits in flight per element: EPT * SPU independent loads
+template <int EPT, int SPU>
+__global__ void __launch_bounds__(WR_THREADS) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int co,
+                                                                  int ktaps, int ci, int ci_b, int fold_up,
+                                                                  int co_begin, int co_count, int ci_total, int ci_off,
+                                                                  const float* __restrict__ inv_scale,
+                                                                  float* __restrict__ out, int accumulate) {
   const int KK = fold_up ? 9 : ktaps;
-  __shared__ float tile[9][WR_CI + 1];
-  const int o = blockIdx.y, c0 = blockIdx.x * WR_CI;
-  const int t = threadIdx.x;
+  __shared__ float tile[9 * WR_PITCH];
+  const int o = blockIdx.y, c0 = blockIdx.x * ci_b;
+  const int nc = min(ci_b, ci - c0);
   pdl_sync();
   const float s = inv_scale ? *inv_scale : 1.0f;
   const int64_t split_stride = (int64_t)co * ktaps * ci;
-  if (t < KK * WR_CI) {
-    const int kk = t / WR_CI, c = t % WR_CI;
-    float acc = 0.f;
-    if (c0 + c < ci) {
-      const float* base = ws + ((int64_t)(co_begin + o) * ktaps) * ci + c0 + c;
-      if (fold_up) {
-        const int ky = kk / 3, kx = kk % 3;
-        for (int a = 0; a < 2; ++a)
-          for (int b = 0; b < 2; ++b) {
-            const int kt = (a * 2 + b) * 4 + up_tap_i(a, ky) * 2 + up_tap_i(b, kx);
-            for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kt * ci];
-          }
-      } else {
-        for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kk * ci];
-      }
+  const float* base0 = ws + ((int64_t)(co_begin + o) * ktaps) * ci + c0;
+  if (fold_up) {
+    for (int e = threadIdx.x; e < KK * nc; e += WR_THREADS) {
+      const int kk = e / nc, c = e - kk * nc;
+      const float* base = base0 + c;
+      float acc = 0.f;
+      const int ky = kk / 3, kx = kk % 3;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int kt = (a * 2 + b) * 4 + up_tap_i(a, ky) * 2 + up_tap_i(b, kx);
+          for (int sp = 0; sp < splits; ++sp) acc += base[(int64_t)sp * split_stride + (int64_t)kt * ci];
+        }
+      tile[kk * WR_PITCH + c] = acc * s;
     }
-    tile[kk][c] = acc * s;
+  } else {
+    // the loads of SPU splits x EPT elements are issued before the first add (an element-at-a-time loop left one round
+    // trip to DRAM per element, or per split, on the critical path); the sums keep the split order
+    const int total = KK * nc;
+    int offs[EPT], tidx[EPT];
+    float acc[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int e = threadIdx.x + i * WR_THREADS;
+      const int ee = e < total ? e : 0;
+      const int kk = ee / nc, c = ee - kk * nc;
+      offs[i] = kk * ci + c;
+      tidx[i] = kk * WR_PITCH + c;
+      acc[i] = 0.f;
+    }
+    const float* bp = base0;
+    int sp = 0;
+    for (; sp + SPU <= splits; sp += SPU, bp += (int64_t)SPU * split_stride) {
+      float v[SPU][EPT];
+#pragma unroll
+      for (int u = 0; u < SPU; ++u)
+#pragma unroll
+        for (int i = 0; i < EPT; ++i)
+          v[u][i] = threadIdx.x + i * WR_THREADS < total ? __ldg(bp + (int64_t)u * split_stride + offs[i]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < SPU; ++u)
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) acc[i] += v[u][i];
+    }
+    for (; sp < splits; ++sp, bp += split_stride) {
+      float v[EPT];
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) v[i] = threadIdx.x + i * WR_THREADS < total ? __ldg(bp + offs[i]) : 0.f;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (threadIdx.x + i * WR_THREADS < total) tile[tidx[i]] = acc[i] * s;
   }
   __syncthreads();
-  if (t < KK * WR_CI) {
-    const int c = t / KK, kk = t % KK;
-    if (c0 + c < ci) {
-      float* op = out + ((int64_t)o * ci_total + ci_off + c0 + c) * KK + kk;
-      const float v = tile[kk][c];
-      *op = accumulate ? *op + v : v;
-    }
+  float* obase = out + ((int64_t)o * ci_total + ci_off + c0) * KK;
+  for (int e = threadIdx.x; e < KK * nc; e += WR_THREADS) {
+    const int c = e / KK, kk = e - c * KK;
+    const float v = tile[kk * WR_PITCH + c];
+    obase[e] = accumulate ? obase[e] + v : v;
   }
 }
 
@@ -526,9 +562,23 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
   }
   launch_k(wgrad_kernel, dim3((unsigned)splits, (unsigned)items), dim3(WG_THREADS), smem_bytes, st, maps, p);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/tcgen05");
-  launch_k(wgrad_reduce_kernel, dim3((unsigned)ceil_div(a->cin, WR_CI), (unsigned)a->cout), dim3(WR_CI * KK), 0, st,
-           (const float*)p.ws, splits, a->cout, p.ktaps, a->cin, a->mode == 2 ? 1 : 0, 0, a->cout, a->ci_total, a->ci_off,
-           a->inv_scale, a->grad, a->accumulate);
+  // ci_b: as wide as possible (more loads in flight per thread) while the grid still fills the machine
+  int ci_b = WR_CI_MAX;
+  while (ci_b > 64 && (int64_t)ceil_div(a->cin, ci_b) * a->cout < 2 * 148) ci_b >>= 1;
+  {
+    const int kk_out = a->mode == 2 ? 9 : p.ktaps;
+    const int ept = ceil_div(kk_out * (ci_b < a->cin ? ci_b : a->cin), WR_THREADS);
+    const dim3 rgrid((unsigned)ceil_div(a->cin, ci_b), (unsigned)a->cout);
+#define DSG_WR_LAUNCH(E, U)                                                                                          \
+    launch_k(wgrad_reduce_kernel<E, U>, rgrid, dim3(WR_THREADS), 0, st, (const float*)p.ws, splits, a->cout, p.ktaps,  \
+             a->cin, ci_b, a->mode == 2 ? 1 : 0, 0, a->cout, a->ci_total, a->ci_off, a->inv_scale, a->grad,            \
+             a->accumulate)
+    if (ept <= 1) DSG_WR_LAUNCH(1, 16);
+    else if (ept <= 3) DSG_WR_LAUNCH(3, 6);
+    else if (ept <= 5) DSG_WR_LAUNCH(5, 4);
+    else DSG_WR_LAUNCH(9, 2);
+#undef DSG_WR_LAUNCH
+  }
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/reduce");
   return DSG_OK;
 }

@@ -622,13 +622,12 @@ class _Program:
                                                       "time_embed"))
         c0 = eng.cfg["block_out_channels"][0]
         x = self._new("conv_in", hw, c0)
-        ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(), b, self.cin, hw[0], hw[1], c0)
+        # conv_in writes the per-channel GroupNorm totals of its output itself (tensor-core form; other widths fall
+        # back to the CUDA-core kernel + one statistics pass inside the same entry point)
+        ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(),
+                   self.stats_of[x.data_ptr()].data_ptr(), b, self.cin, hw[0], hw[1], c0)
         self._emit("conv_in", {"bytes": b * hw[0] * hw[1] * (self.cin * 4 + c0 * 2)},
-                   lambda st: check(lib.dsg_conv_in(self.in_ptr, *ci_args, st), "conv_in"))
-        # conv_in is a CUDA-core kernel without the statistics epilogue: one read of its output instead
-        gs_args = (x.data_ptr(), c0, self.stats_of[x.data_ptr()].data_ptr(), b, hw[0] * hw[1])
-        self._emit("gn_stats", {"bytes": b * hw[0] * hw[1] * c0 * 2},
-                   lambda st: check(lib.dsg_gn_stats(*gs_args, st), "gn_stats"))
+                   lambda st: check(lib.dsg_conv_in_stats(self.in_ptr, *ci_args, st), "conv_in"))
         self._record({"kind": "in", "out": x, "hw": hw, "c0": c0})
         skips = [(x, c0, hw)]
         for i, blk in enumerate(eng.down):

@@ -82,6 +82,19 @@ def conv_in(x_nchw, w, b):
     return out
 
 
+def conv_in_stats(x_nchw, w, b):
+    """conv_in + the per-channel GroupNorm totals of its output (int64 [n,cout,2], see gn_stats)."""
+    _cuda(x_nchw, w, b)
+    lib = _lib.load()
+    n, cin, h, wd = x_nchw.shape
+    cout = w.shape[0]
+    out = torch.empty((n, h, wd, cout), dtype=torch.float16, device=x_nchw.device)
+    st = torch.zeros((n, cout, 2), dtype=torch.int64, device=x_nchw.device)
+    check(lib.dsg_conv_in_stats(x_nchw.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), st.data_ptr(), n, cin, h,
+                                wd, cout, _st(x_nchw)), "conv_in_stats")
+    return out, st
+
+
 def conv_out(x_nhwc, w, b):
     _cuda(x_nhwc, w, b)
     lib = _lib.load()

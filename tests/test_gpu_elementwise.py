@@ -171,6 +171,37 @@ def test_conv_in_out_vs_torch():
     assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4), (got - ref).abs().max()  # fp32 math on both sides
 
 
+@pytest.mark.parametrize("n,cin,cout,h,w", [(2, 3, 64, 20, 28), (3, 3, 64, 64, 64), (1, 3, 64, 13, 37), (2, 1, 64, 8, 8),
+                                            (16, 3, 64, 256, 256), (2, 3, 64, 9, 512), (2, 3, 128, 16, 16),
+                                            (2, 4, 64, 16, 16)])
+def test_conv_in_stats_tensor_core_form_vs_torch(n, cin, cout, h, w):
+    """dsg_conv_in_stats: mma.sync form (cout 64, cin*9 <= 32; fp16 operands, fp32 accumulate) and the fall-back for
+    other widths, against torch fp32 conv2d; the fused statistics against sums of the fp32 reference output."""
+    from drivescenegen_b200 import ops
+    torch.manual_seed(3)
+    d = _dev()
+    x = torch.randn(n, cin, h, w)
+    ci = torch.nn.Conv2d(cin, cout, 3, padding=1)
+    with torch.no_grad():
+        ref = ci.to(d)(x.to(d)).float().cpu()
+    got, st = ops.conv_in_stats(x.to(d), ci.weight.detach().to(d), ci.bias.detach().to(d))
+    got = got.float().permute(0, 3, 1, 2).cpu()
+    # fp16 rounding of x, w (2^-11 each, 27 terms) and of the output
+    assert torch.allclose(got, ref, atol=6e-3, rtol=4e-3), (got - ref).abs().max()
+    assert ((got - ref).norm() / ref.norm()).item() < 1.5e-3
+    st = st.cpu().double()
+    s_ref = ref.double().sum(dim=(2, 3))
+    q_ref = (ref.double() ** 2).sum(dim=(2, 3))
+    s_got, q_got = st[..., 0] / 2 ** 24, st[..., 1] / 2 ** 20
+    npx = h * w
+    assert (s_got - s_ref).abs().max().item() <= 2e-3 * npx ** 0.5 + 1e-3 * s_ref.abs().max().item()
+    assert ((q_got - q_ref).abs() / q_ref).max().item() < 5e-3
+    # and they agree with a separate statistics pass over the stored fp16 tensor
+    got16, _ = ops.conv_in_stats(x.to(d), ci.weight.detach().to(d), ci.bias.detach().to(d))
+    st2 = ops.gn_stats(got16).cpu().double()
+    assert ((st2[..., 1] - st[..., 1]).abs() / st[..., 1]).max().item() < 2e-3
+
+
 @pytest.mark.parametrize("c1,c2,hw", [(64, 0, (32, 32)), (128, 64, (16, 16)), (512, 256, (8, 8)), (256, 128, (12, 20)),
                                       (1024, 0, (8, 8))])
 @pytest.mark.parametrize("act", [0, 1])
