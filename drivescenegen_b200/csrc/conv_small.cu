@@ -12,13 +12,15 @@ constexpr int CS_THREADS = 256;
 constexpr int CI_PX = 4;
 __global__ void __launch_bounds__(CS_THREADS, 2) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ b, __half* __restrict__ out,
-                                                             int n, int cin, int h, int wd, int cout) {
+                                                             int n, int cin, int h, int wd, int cout,
+                                                             const float* __restrict__ xscale) {
   extern __shared__ float sw[];  // [cin*9][cout] then bias[cout]
   const int K = cin * 9;
   pdl_sync();
+  const float xs = xscale ? *xscale : 1.0f;   // a power of two folded into the weights: exact
   for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
     const int k = i / cout, co = i - k * cout;  // w is [cout][cin][3][3] = [cout][K]
-    sw[i] = w[co * K + k];
+    sw[i] = w[co * K + k] * xs;
   }
   float* sb = sw + K * cout;
   for (int i = threadIdx.x; i < cout; i += blockDim.x) sb[i] = b[i];
@@ -116,7 +118,8 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
                                                                       const float* __restrict__ b,
                                                                       __half* __restrict__ out,
                                                                       long long* __restrict__ stats, int n, int cin,
-                                                                      int h, int wd) {
+                                                                      int h, int wd,
+                                                                      const float* __restrict__ xscale) {
   extern __shared__ __align__(16) unsigned char cm_smem[];
   const int P = (wd + 2 + 15) & ~15;          // window pitch (halves): column 0 = image column -1; the tail is zero
   const int plane = (CM_ROWS + 2) * P;
@@ -136,6 +139,8 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
     s_in[(cin + 1) * plane + i] = __float2half_rn(0.f);
   }
   pdl_sync();
+  // optional power-of-two input scale (conv_out's data gradient: the raw loss gradient is far below fp16 range)
+  const float xs = xscale ? *xscale : 1.0f;
   // B fragments: b0 = W[k = 16s + 2t, 2t + 1][n = 8j + g], b1 = W[k + 8, k + 9][n]; W[k][n] = w[n][k] (OIHW, k < K)
   uint32_t bf[2][CM_NT][2];
 #pragma unroll
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int c = c0 + u * 32 + lane;
-          if (c < P) sp[c] = __float2half_rn(v[u]);
+          if (c < P) sp[c] = __float2half_rn(v[u] * xs);
         }
       }
     }
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
         }
       }
     __syncthreads();
-    if (threadIdx.x < 128) {
+    if (stats != nullptr && threadIdx.x < 128) {
       const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
       float tot = 0.f;
 #pragma unroll
@@ -350,8 +355,11 @@ using namespace dsg;
 
 extern "C" {
 
-int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, int32_t n, int32_t cin, int32_t h,
-                int32_t wd, int32_t cout, void* stream) {
+static int launch_conv_in_mma(const float* x, const float* xscale, const float* w, const float* b, void* out_h16,
+                              void* stats, int n, int cin, int h, int wd, int cout, cudaStream_t st);
+
+static int conv_in_f32(const float* x, const float* xscale, const float* w, const float* b, void* out_h16, int32_t n,
+                       int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream) {
   DSG_CHECK_ARG(x && w && b && out_h16, "dsg_conv_in: null pointer");
   DSG_CHECK_ARG(cin >= 1 && cin <= 4 && cout % 8 == 0 && cout >= 8 && cout <= 512, "dsg_conv_in: cin<=4, cout%%8==0");
   DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_in: bad shape");
@@ -364,9 +372,48 @@ int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, i
   int64_t blocks = ceil_div64(total_q, qpb);
   if (blocks > 148 * 2) blocks = 148 * 2;  // persistent: the weight staging is paid once per block
   launch_k(conv_in_kernel, dim3((unsigned)blocks), dim3(CS_THREADS), sm, (cudaStream_t)stream, x, w, b,
-           (__half*)out_h16, n, cin, h, wd, cout);
+           (__half*)out_h16, n, cin, h, wd, cout, xscale);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_in");
   return DSG_OK;
+}
+
+int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, int32_t n, int32_t cin, int32_t h,
+                int32_t wd, int32_t cout, void* stream) {
+  return conv_in_f32(x, nullptr, w, b, out_h16, n, cin, h, wd, cout, stream);
+}
+
+int dsg_conv_in_scaled(const float* x, const float* xscale, const float* w, const float* b, void* out_h16, int32_t n,
+                       int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream) {
+  DSG_CHECK_ARG(x && xscale && w && b && out_h16, "dsg_conv_in_scaled: null pointer");
+  DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_in_scaled: bad shape");
+  if (n == 0) return DSG_OK;
+  if (launch_conv_in_mma(x, xscale, w, b, out_h16, nullptr, n, cin, h, wd, cout, (cudaStream_t)stream) == 0) {
+    DSG_CUDA_LAUNCH_CHECK("dsg_conv_in_scaled");
+    return DSG_OK;
+  }
+  return conv_in_f32(x, xscale, w, b, out_h16, n, cin, h, wd, cout, stream);
+}
+
+// tensor-core form when the shape allows it; returns 1 when it does not
+static int launch_conv_in_mma(const float* x, const float* xscale, const float* w, const float* b, void* out_h16,
+                              void* stats, int n, int cin, int h, int wd, int cout, cudaStream_t st) {
+  const size_t sm = (size_t)(cin + 2) * (CM_ROWS + 2) * ((wd + 2 + 15) & ~15) * 2 + CM_ROWS * 64 * 2 * sizeof(float) +
+                    CM_ROWS * 16 * CM_OPITCH;
+  if (!(cout == 64 && cin >= 1 && cin * 9 + 2 <= 32 && sm <= 100 * 1024 && (uintptr_t)out_h16 % 16 == 0)) return 1;
+  const int64_t items = (int64_t)n * ((h + CM_ROWS - 1) / CM_ROWS);
+  const int64_t blocks = items < 148 * 2 ? items : 148 * 2;  // persistent: weights are loaded once per block
+  if (wd % 16 == 0) {
+    if (sm > 48 * 1024)
+      cudaFuncSetAttribute(conv_in_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    launch_k(conv_in_mma_kernel<true>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, st, x, w, b, (__half*)out_h16,
+             (long long*)stats, n, cin, h, wd, xscale);
+  } else {
+    if (sm > 48 * 1024)
+      cudaFuncSetAttribute(conv_in_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    launch_k(conv_in_mma_kernel<false>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, st, x, w, b, (__half*)out_h16,
+             (long long*)stats, n, cin, h, wd, xscale);
+  }
+  return 0;
 }
 
 int dsg_conv_in_stats(const float* x, const float* w, const float* b, void* out_h16, void* stats, int32_t n,
@@ -374,22 +421,7 @@ int dsg_conv_in_stats(const float* x, const float* w, const float* b, void* out_
   DSG_CHECK_ARG(x && w && b && out_h16 && stats, "dsg_conv_in_stats: null pointer");
   DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_in_stats: bad shape");
   if (n == 0) return DSG_OK;
-  const size_t sm = (size_t)(cin + 2) * (CM_ROWS + 2) * ((wd + 2 + 15) & ~15) * 2 + CM_ROWS * 64 * 2 * sizeof(float) +
-                    CM_ROWS * 16 * CM_OPITCH;
-  if (cout == 64 && cin >= 1 && cin * 9 + 2 <= 32 && sm <= 100 * 1024 && (uintptr_t)out_h16 % 16 == 0) {
-    const int64_t items = (int64_t)n * ((h + CM_ROWS - 1) / CM_ROWS);
-    const int64_t blocks = items < 148 * 2 ? items : 148 * 2;  // persistent: weights are loaded once per block
-    if (wd % 16 == 0) {
-      if (sm > 48 * 1024)
-        cudaFuncSetAttribute(conv_in_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      launch_k(conv_in_mma_kernel<true>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, (cudaStream_t)stream, x, w, b,
-               (__half*)out_h16, (long long*)stats, n, cin, h, wd);
-    } else {
-      if (sm > 48 * 1024)
-        cudaFuncSetAttribute(conv_in_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      launch_k(conv_in_mma_kernel<false>, dim3((unsigned)blocks), dim3(CM_ROWS * 32), sm, (cudaStream_t)stream, x, w, b,
-               (__half*)out_h16, (long long*)stats, n, cin, h, wd);
-    }
+  if (launch_conv_in_mma(x, nullptr, w, b, out_h16, stats, n, cin, h, wd, cout, (cudaStream_t)stream) == 0) {
     DSG_CUDA_LAUNCH_CHECK("dsg_conv_in_stats");
     return DSG_OK;
   }

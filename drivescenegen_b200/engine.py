@@ -81,6 +81,10 @@ class UNetEngine:
         # convs slow down by more than the removed GroupNorm pass costs.  Kept as an opt-in for experiments:
         # DSG_FUSE_GN = 0 (default) never, 1 = convs with 256-wide tiles only, 2 = wherever the kernel supports it.
         self.fuse_gn = int(os.environ.get("DSG_FUSE_GN", "0"))
+        # samples per L2 group for the full-resolution ops of the sampling program (0 = whole batch per launch):
+        # the level-0 tensors of a 16-sample batch are 134 MB each (> the 126 MB L2), those of a 2-4 sample group are
+        # not, so running conv -> GroupNorm -> conv ... group by group lets each consumer find its input in L2
+        self.l2_group = int(os.environ.get("DSG_L2_GROUP", "0"))
         self.train_packs = False  # also pack the data-gradient forms of every conv weight (training path)
         self.train_programs: Dict[Tuple[int, int, int, int], object] = {}
         self._build_topology()
@@ -423,8 +427,37 @@ class _Program:
         self.stats_all = eng.arena.get(f"{batch}x{h}x{w}/gn_stats", max(self._stats_off, 2), torch.int64)
         self._stats_off = 0
         self.stats_of = {}
-        self.ops, self.keep, self.op_info = [], [], []
+        self.ops, self.keep, self.op_info, self.op_sub = [], [], [], []
         self._build()
+        g = int(getattr(eng, "l2_group", 0))
+        if self.regroup and g and g < self.b and self.b % g == 0:
+            self._regroup(g)
+
+    regroup = True   # the training program (engine_train.TrainProgram) keeps whole-batch launches
+
+    def _regroup(self, g: int):
+        """Re-issue every run of consecutive full-resolution ops sample-group by sample-group (depth first): all of
+        the U-Net is independent per sample, so the result is bit-identical; only the order of launches changes."""
+        full = self.h * self.w
+        ops, info = [], []
+        i, n = 0, len(self.ops)
+        while i < n:
+            j = i
+            while j < n and self.op_sub[j][0] is not None and self.op_sub[j][1] >= full:
+                j += 1
+            if j - i < 2:
+                ops.append(self.ops[i]); info.append(self.op_info[i])
+                i += 1
+                continue
+            for n0 in range(0, self.b, g):
+                for k in range(i, j):
+                    name, meta = self.op_info[k]
+                    ops.append(self.op_sub[k][0](n0, g))
+                    info.append((name, {kk: (v * g // self.b if kk in ("flops", "bytes") else v)
+                                        for kk, v in meta.items()}))
+            i = j
+        self.ops, self.op_info = ops, info
+        self.n_launches = len(self.ops) + 1
 
     # --- buffers -------------------------------------------------------------------------------------
     def _stats(self, ch: int) -> torch.Tensor:
@@ -458,9 +491,12 @@ class _Program:
         return None   # inference keeps no time-embedding activations (the training program does)
 
     # --- op emitters ---------------------------------------------------------------------------------
-    def _emit(self, name: str, meta: dict, fn: Callable[[int], None]):
+    def _emit(self, name: str, meta: dict, fn: Callable[[int], None], sub=None, px: int = 0):
+        """sub(n0, ng) -> the same op restricted to samples [n0, n0 + ng) (or None); px = pixels per sample it touches."""
         self.ops.append(fn)
         self.op_info.append((name, meta))
+        if hasattr(self, "op_sub"):
+            self.op_sub.append((sub, px))
 
     def _gn_stats_for(self, x1, c1, x2, c2, hw, st1=None, st2=None):
         """the statistics a GroupNorm over cat(x1, x2) reads: accumulated by whoever produced x1 / x2, or — odd group
@@ -491,7 +527,20 @@ class _Program:
         a2 = (_p(x1), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps, act,
               out.data_ptr(), b, npx, eng.groups)
         nbytes = b * npx * (c1 + c2) * 2
-        self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"))
+
+        def sub(n0, ng, a=a2):
+            a = list(a)
+            a[0] += n0 * npx * c1 * 2
+            a[2] += n0 * c1 * 16
+            if x2 is not None:
+                a[3] += n0 * npx * c2 * 2
+                a[5] += n0 * c2 * 16
+            a[10] += n0 * npx * (c1 + c2) * 2
+            a[11] = ng
+            a = tuple(a)
+            return lambda st: check(lib.dsg_gn_apply(*a, st), "gn_apply")
+        self._emit("gn_apply", {"bytes": 2 * nbytes}, lambda st, a=a2: check(lib.dsg_gn_apply(*a, st), "gn_apply"),
+                   sub=sub, px=npx)
         return st1, st2
 
     def _gn_coef(self, x1, c1, x2, c2, hw, gname, bname, st1=None, st2=None) -> torch.Tensor:
@@ -542,7 +591,42 @@ class _Program:
         opx = {0: hw[0] * hw[1], 1: hw[0] * hw[1] // 4, 2: hw[0] * hw[1] * 4, 3: hw[0] * hw[1]}[mode]
         meta = {"mode": mode, "hw": hw, "cin": cin + csc1 + csc2, "cout": cout,
                 "flops": 2 * self.b * opx * cout * k_ref}  # algorithmic (reference op count, no sub-pixel discount)
-        self._emit("conv", meta, lambda st, r=ref: check(lib.dsg_conv(r, st), f"conv {wname}"))
+        sub = None
+        if gn_coef is None:
+            def sub(n0, ng, a=a):
+                return self._conv_sub(a, n0, ng, opx, f"conv {wname}")
+        self._emit("conv", meta, lambda st, r=ref: check(lib.dsg_conv(r, st), f"conv {wname}"), sub=sub,
+                   px=max(opx, hw[0] * hw[1]))
+
+    def _conv_sub(self, a: ConvArgs, n0: int, ng: int, opx: int, what: str, out_f32_of=None):
+        """dsg_conv of `a` restricted to samples [n0, n0 + ng): a copy of the argument block with shifted pointers."""
+        lib = self.lib
+        s = ConvArgs.from_buffer_copy(a)
+        ipx = a.h * a.w
+        s.n = ng
+        s.x = a.x + n0 * ipx * a.cin * 2
+        if a.sc1:
+            s.sc1 = a.sc1 + n0 * ipx * a.csc1 * 2
+        if a.sc2:
+            s.sc2 = a.sc2 + n0 * ipx * a.csc2 * 2
+        if a.temb:
+            s.temb = a.temb + n0 * a.temb_stride * 4
+        if a.residual:
+            s.residual = a.residual + n0 * opx * a.cout * 2
+        if a.out:
+            s.out = a.out + n0 * opx * a.cout * 2
+        if a.out_stats:
+            s.out_stats = a.out_stats + n0 * a.cout * 16
+        self.keep.append(s)
+        r = C.byref(s)
+        if out_f32_of is None:
+            return lambda st: check(lib.dsg_conv(r, st), what)
+        off = n0 * a.cout_real * opx * 4
+
+        def run(st):
+            s.out_nchw_f32 = out_f32_of().value + off
+            check(lib.dsg_conv(r, st), what)
+        return run
 
     def _resnet(self, r, x1, x2, hw, out):
         c1, c2, co, pre = r["cin"], r["cskip"], r["cout"], r["prefix"]
@@ -626,8 +710,14 @@ class _Program:
         # back to the CUDA-core kernel + one statistics pass inside the same entry point)
         ci_args = (W["conv_in.w"].data_ptr(), W["conv_in.b"].data_ptr(), x.data_ptr(),
                    self.stats_of[x.data_ptr()].data_ptr(), b, self.cin, hw[0], hw[1], c0)
+        def conv_in_sub(n0, ng, a=ci_args):
+            npx = hw[0] * hw[1]
+            a2 = (a[0], a[1], a[2] + n0 * npx * c0 * 2, a[3] + n0 * c0 * 16, ng) + a[5:]
+            off = n0 * self.cin * npx * 4
+            return lambda st: check(lib.dsg_conv_in_stats(C.c_void_p(self.in_ptr.value + off), *a2, st), "conv_in")
         self._emit("conv_in", {"bytes": b * hw[0] * hw[1] * (self.cin * 4 + c0 * 2)},
-                   lambda st: check(lib.dsg_conv_in_stats(self.in_ptr, *ci_args, st), "conv_in"))
+                   lambda st: check(lib.dsg_conv_in_stats(self.in_ptr, *ci_args, st), "conv_in"),
+                   sub=conv_in_sub, px=hw[0] * hw[1])
         self._record({"kind": "in", "out": x, "hw": hw, "c0": c0})
         skips = [(x, c0, hw)]
         for i, blk in enumerate(eng.down):
@@ -706,7 +796,11 @@ class _Program:
             def run_conv_out(st, a=a):
                 a.out_nchw_f32 = self.out_ptr.value
                 check(lib.dsg_conv(C.byref(a), st), "conv_out (tcgen05)")
-            self._emit("conv_out", meta, run_conv_out)
+            co_sub = None
+            if not fuse_out:
+                def co_sub(n0, ng, a=a):
+                    return self._conv_sub(a, n0, ng, hw[0] * hw[1], "conv_out (tcgen05)", out_f32_of=lambda: self.out_ptr)
+            self._emit("conv_out", meta, run_conv_out, sub=co_sub, px=hw[0] * hw[1])
         else:
             co_args = (act.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
             co_tail = (b, c0, hw[0], hw[1], self.cout)

@@ -27,6 +27,8 @@ from .engine import UNetEngine, _Program, _p
 
 
 class TrainProgram(_Program):
+    regroup = False   # whole-batch launches: the backward op list is built against the forward's whole-batch buffers
+
     def __init__(self, eng: UNetEngine, batch: int, h: int, w: int, grad_slices: Dict[str, torch.Tensor]):
         """grad_slices: parameter name (upstream state-dict key) -> fp32 view that receives its gradient."""
         self.grads = grad_slices
@@ -258,10 +260,10 @@ class TrainProgram(_Program):
                 dout = self.dout_ptr
                 check(lib.dsg_grad_scale(dout, numel, amax_partial.data_ptr(), amax_parts, self.scale_ptr, st),
                       "grad_scale")
-                check(lib.dsg_conv_out_dgrad_weight(w_out.data_ptr(), self.cout, c0, self.scale_ptr, wt.data_ptr(), st),
+                check(lib.dsg_conv_out_dgrad_weight(w_out.data_ptr(), self.cout, c0, None, wt.data_ptr(), st),
                       "conv_out_dgrad_weight")
-                check(lib.dsg_conv_in(dout, wt.data_ptr(), zero_b.data_ptr(), dact.data_ptr(), b, self.cout, hw[0],
-                                      hw[1], c0, st), "conv_out dgrad")
+                check(lib.dsg_conv_in_scaled(dout, self.scale_ptr, wt.data_ptr(), zero_b.data_ptr(), dact.data_ptr(), b,
+                                             self.cout, hw[0], hw[1], c0, st), "conv_out dgrad")
                 check(lib.dsg_small_wgrad(act.data_ptr(), dout, b, hw[0], hw[1], c0, self.cout, 1,
                                           sw_partial.data_ptr(), sw_parts, None, G["conv_out.weight"].data_ptr(),
                                           G["conv_out.bias"].data_ptr(), st), "conv_out wgrad")

@@ -333,9 +333,16 @@ def conv_out_dgrad(dout_nchw, w, scale=None):
     lib = _lib.load()
     cout, cin = w.shape[0], w.shape[1]
     wt = torch.empty((cin, cout, 3, 3), dtype=torch.float32, device=w.device)
-    check(lib.dsg_conv_out_dgrad_weight(w.contiguous().data_ptr(), cout, cin, _p(scale), wt.data_ptr(), _st(w)),
+    check(lib.dsg_conv_out_dgrad_weight(w.contiguous().data_ptr(), cout, cin, None, wt.data_ptr(), _st(w)),
           "conv_out_dgrad_weight")
-    return conv_in(dout_nchw, wt, torch.zeros(cin, dtype=torch.float32, device=w.device))
+    zero_b = torch.zeros(cin, dtype=torch.float32, device=w.device)
+    if scale is None:
+        return conv_in(dout_nchw, wt, zero_b)
+    n, _, h, wd = dout_nchw.shape
+    out = torch.empty((n, h, wd, cin), dtype=torch.float16, device=w.device)
+    check(lib.dsg_conv_in_scaled(dout_nchw.data_ptr(), scale.data_ptr(), wt.data_ptr(), zero_b.data_ptr(), out.data_ptr(),
+                                 n, cout, h, wd, cin, _st(w)), "conv_in_scaled")
+    return out
 
 
 def small_wgrad(wide, narrow, conv_out_form: bool, inv_scale=None):

@@ -98,6 +98,11 @@ int dsg_time_embed(const float* t, const float* freqs, int32_t half, int32_t fli
 /* conv_in: NCHW fp32 [n][cin][h][w] (cin <= 4) -> h16 [n][h][w][cout]; 3x3, pad 1.  w: fp32 [cout][cin][3][3]. */
 int dsg_conv_in(const float* x, const float* w, const float* b, void* out_h16, int32_t n, int32_t cin, int32_t h,
                 int32_t wd, int32_t cout, void* stream);
+/* dsg_conv_in on (*xscale) * x, xscale a device pointer to a power of two: conv_out's data gradient, whose fp32 input
+ * (the raw loss gradient) is far below fp16 range.  cout == 64, cin <= 3: tensor cores (x * xscale rounded to fp16);
+ * other shapes: the fp32 CUDA-core kernel with the scale folded into the weights. */
+int dsg_conv_in_scaled(const float* x, const float* xscale, const float* w, const float* b, void* out_h16, int32_t n,
+                       int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream);
 /* conv_in + the per-channel GroupNorm totals of its output (same int64 fixed-point format as dsg_gn_stats; added to
  * `stats`, which the caller zeroes): cout == 64 and cin <= 3 run on the tensor cores (mma.sync, fp16 operands,
  * fp32 accumulate) with the statistics fused; any other shape = dsg_conv_in followed by dsg_gn_stats. */

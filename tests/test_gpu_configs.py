@@ -90,3 +90,27 @@ def test_run_from_host_pipelined_equals_serial_loop():
             assert torch.equal(o, ref), f"step {i} differs"
     with pytest.raises(ValueError):
         sess.run_from_host(ts, noise, outs[:1])
+
+
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_l2_sample_groups_are_bit_identical_to_whole_batch_launches(group):
+    """engine.l2_group re-issues the full-resolution ops sample-group by sample-group (depth first) so consumers find
+    their inputs in L2; every op of the U-Net is independent per sample, so the output must not change by a bit."""
+    from drivescenegen_b200.hostapi import UNet2DModel
+    torch.manual_seed(0)
+    model = UNet2DModel(sample_size=64, **REF_CFG).to(_dev()).eval()
+    x = torch.randn(8, 3, 64, 64, generator=torch.Generator().manual_seed(9)).to(_dev())
+    eng = model.engine()
+    eng.l2_group = 0
+    eng.programs.clear()
+    with torch.no_grad():
+        ref = model(x, 321).sample.clone()
+        n0 = eng.program(8, 64, 64).n_launches
+        eng.l2_group = group
+        eng.programs.clear()
+        got = model(x, 321).sample.clone()
+        n1 = eng.program(8, 64, 64).n_launches
+    eng.l2_group = 0
+    eng.programs.clear()
+    assert n1 > n0
+    assert torch.equal(got, ref)
