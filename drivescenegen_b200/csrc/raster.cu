@@ -25,24 +25,36 @@ __global__ void __launch_bounds__(256) image_to_sample_kernel(const uint8_t* __r
   const uint8_t* src = img + (int64_t)n * hw * C_IMG;
   float* dst = out + (int64_t)n * c_out * hw;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads_per_image; q += stride) {
-    uint32_t words[C_IMG];
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + q * 4 * C_IMG);
+  constexpr int UQ = 4;   // quads per thread per iteration: UQ * C_IMG independent loads in flight
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads_per_image; q0 += stride * UQ) {
+    uint32_t words[UQ][C_IMG];
 #pragma unroll
-    for (int i = 0; i < C_IMG; ++i) words[i] = __ldg(wp + i);
+    for (int u = 0; u < UQ; ++u) {
+      const int64_t q = q0 + u * stride;
+      if (q < quads_per_image) {
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + q * 4 * C_IMG);
 #pragma unroll
-    for (int ch = 0; ch < C_IMG; ++ch) {
-      if (ch >= c_out) break;
-      float4 v;
-      float* vp = reinterpret_cast<float*>(&v);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int b = p * C_IMG + ch;  // byte index inside the 4-pixel group
-        const float x = (float)((words[b >> 2] >> ((b & 3) * 8)) & 0xffu);
-        // ToTensor: x.to(float32).div(255); Normalize: sub(mean).div(std) -- three separately rounded fp32 operations
-        vp[p] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.0f), 0.5f), 0.5f);
+        for (int i = 0; i < C_IMG; ++i) words[u][i] = __ldg(wp + i);
       }
-      *reinterpret_cast<float4*>(dst + (int64_t)ch * hw + q * 4) = v;
+    }
+#pragma unroll
+    for (int u = 0; u < UQ; ++u) {
+      const int64_t q = q0 + u * stride;
+      if (q >= quads_per_image) break;
+#pragma unroll
+      for (int ch = 0; ch < C_IMG; ++ch) {
+        if (ch >= c_out) break;
+        float4 v;
+        float* vp = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int b = p * C_IMG + ch;  // byte index inside the 4-pixel group
+          const float x = (float)((words[u][b >> 2] >> ((b & 3) * 8)) & 0xffu);
+          // ToTensor: x.to(float32).div(255); Normalize: sub(mean).div(std) -- three separately rounded fp32 operations
+          vp[p] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.0f), 0.5f), 0.5f);
+        }
+        *reinterpret_cast<float4*>(dst + (int64_t)ch * hw + q * 4) = v;
+      }
     }
   }
 }
@@ -198,27 +210,40 @@ __global__ void __launch_bounds__(256) gray_mask_kernel(const uint8_t* __restric
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
     const int64_t quads = hw / 4;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + tid; q < quads; q += stride) {
-      uint32_t words[4];
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + q * 4 * c);
-      for (int i = 0; i < c; ++i) words[i] = __ldg(wp + i);
-      uint32_t out = 0;
+    constexpr int UQ = 4;
+    for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + tid; q0 < quads; q0 += stride * UQ) {
+      uint32_t words[UQ][4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int b0 = p * c, b1 = p * c + 1;
-        const int r = (words[b0 >> 2] >> ((b0 & 3) * 8)) & 0xff;
-        const int g = (words[b1 >> 2] >> ((b1 & 3) * 8)) & 0xff;
-        const uint32_t v = (near_peak[0][r] & near_peak[1][g]) ? 0u : 255u;
-        out |= v << (p * 8);
+      for (int u = 0; u < UQ; ++u) {
+        const int64_t q = q0 + u * stride;
+        if (q < quads) {
+          const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + q * 4 * c);
+          words[u][0] = __ldg(wp); words[u][1] = __ldg(wp + 1); words[u][2] = __ldg(wp + 2);
+          words[u][3] = c == 4 ? __ldg(wp + 3) : 0u;
+        }
       }
-      *reinterpret_cast<uint32_t*>(m + q * 4) = out;
-      if (g3) {
-        // 4 pixels x 3 identical channels = 12 bytes: p0 p0 p0 p1 | p1 p1 p2 p2 | p2 p3 p3 p3
-        const uint32_t p0 = out & 0xff, p1 = (out >> 8) & 0xff, p2 = (out >> 16) & 0xff, p3 = out >> 24;
-        uint32_t* gp = reinterpret_cast<uint32_t*>(g3 + q * 12);
-        gp[0] = p0 | (p0 << 8) | (p0 << 16) | (p1 << 24);
-        gp[1] = p1 | (p1 << 8) | (p2 << 16) | (p2 << 24);
-        gp[2] = p2 | (p3 << 8) | (p3 << 16) | (p3 << 24);
+#pragma unroll
+      for (int u = 0; u < UQ; ++u) {
+        const int64_t q = q0 + u * stride;
+        if (q >= quads) break;
+        uint32_t out = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int b0 = p * c, b1 = p * c + 1;
+          const int r = (words[u][b0 >> 2] >> ((b0 & 3) * 8)) & 0xff;
+          const int g = (words[u][b1 >> 2] >> ((b1 & 3) * 8)) & 0xff;
+          const uint32_t v = (near_peak[0][r] & near_peak[1][g]) ? 0u : 255u;
+          out |= v << (p * 8);
+        }
+        *reinterpret_cast<uint32_t*>(m + q * 4) = out;
+        if (g3) {
+          // 4 pixels x 3 identical channels = 12 bytes: p0 p0 p0 p1 | p1 p1 p2 p2 | p2 p3 p3 p3
+          const uint32_t p0 = out & 0xff, p1 = (out >> 8) & 0xff, p2 = (out >> 16) & 0xff, p3 = out >> 24;
+          uint32_t* gp = reinterpret_cast<uint32_t*>(g3 + q * 12);
+          gp[0] = p0 | (p0 << 8) | (p0 << 16) | (p1 << 24);
+          gp[1] = p1 | (p1 << 8) | (p2 << 16) | (p2 << 24);
+          gp[2] = p2 | (p3 << 8) | (p3 << 16) | (p3 << 24);
+        }
       }
     }
   } else {
@@ -249,9 +274,17 @@ __global__ void __launch_bounds__(256) agent_threshold_kernel(const float* __res
   };
   if (vec_ok) {
     const int64_t quads = hw / 4;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + q);
-      *reinterpret_cast<uint32_t*>(dst + q * 4) = one(v.x) | (one(v.y) << 8) | (one(v.z) << 16) | (one(v.w) << 24);
+    constexpr int UQ = 4;
+    for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += stride * UQ) {
+      float4 v[UQ];
+#pragma unroll
+      for (int u = 0; u < UQ; ++u)
+        if (q0 + u * stride < quads) v[u] = __ldg(reinterpret_cast<const float4*>(src) + q0 + u * stride);
+#pragma unroll
+      for (int u = 0; u < UQ; ++u)
+        if (q0 + u * stride < quads)
+          *reinterpret_cast<uint32_t*>(dst + (q0 + u * stride) * 4) =
+              one(v[u].x) | (one(v[u].y) << 8) | (one(v[u].z) << 16) | (one(v[u].w) << 24);
     }
   } else {
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += stride) dst[p] = (uint8_t)one(src[p]);

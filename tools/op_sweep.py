@@ -83,9 +83,7 @@ def main():
         import numpy as np
         rng = np.random.default_rng(0)
         for size in [int(s) for s in args.sizes.split(",")]:
-            for b in (16, 256):
-                if size == 512 and b > 64:
-                    b = 64
+            for b in ((16, 256, 1024) if size <= 256 else (16, 64, 256)):
                 img = rng.integers(0, 256, (b, size, size, 3), dtype=np.uint8)
                 bg = rng.random((b, size, size)) < 0.9          # BEV rasters: one dominant background value
                 img[..., 0] = np.where(bg, 127, img[..., 0])
