@@ -63,3 +63,41 @@ def test_agent_threshold_truncation_cases():
     got = agent_threshold(plane).ravel()
     assert np.array_equal(got, np.where(trunc.ravel() > 100, 255, 0))
     assert got[100] == 0 and got[102] == 255
+
+
+def test_raster_dataset_host_side_and_no_cpu_path(tmp_path):
+    """RasterDataset (Image_Dataset's constructor / data_list / remove_sample; decode only) and the rule that the raster
+    kernels have no CPU fallback: without a CUDA device every entry point raises DsgError."""
+    import types
+
+    import torch
+    from PIL import Image
+
+    from drivescenegen_b200._lib import DsgError
+    from drivescenegen_b200.hostapi import RasterDataset, raster
+    rng = np.random.default_rng(1)
+    imgs = rng.integers(0, 256, (3, 24, 40, 3), dtype=np.uint8)
+    for i, im in enumerate(imgs):
+        Image.fromarray(im).save(tmp_path / f"{i}.png")
+    cfg = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=24, patterns_size_width=40)
+    ds = RasterDataset(cfg)
+    ds.data_list.sort()
+    assert len(ds) == 3
+    item = ds[1]
+    assert item.dtype == torch.uint8 and tuple(item.shape) == (24, 40, 3) and np.array_equal(item.numpy(), imgs[1])
+    ds.remove_sample(0)
+    assert len(ds) == 2 and np.array_equal(ds[0].numpy(), imgs[1])
+    batch = torch.utils.data.default_collate([ds[0], ds[1]])
+    assert raster.is_raster_batch(batch) and not raster.is_raster_batch(batch.float())
+    assert not raster.is_raster_batch(torch.zeros(2, 3, 8, 8))            # a normalised fp32 batch is left alone
+    wrong = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=32, patterns_size_width=32)
+    with pytest.raises(ValueError):
+        RasterDataset(wrong)[0]
+    if not torch.cuda.is_available():
+        for call in (lambda: raster.image_to_sample(imgs), lambda: raster.gray_masks(imgs),
+                     lambda: raster.get_gray_image(Image.fromarray(imgs[0])),
+                     lambda: raster.agent_threshold(torch.zeros(3, 8, 8))):
+            with pytest.raises(DsgError):
+                call()
+    with pytest.raises(ValueError):
+        raster.image_to_sample(imgs.astype(np.float32))
