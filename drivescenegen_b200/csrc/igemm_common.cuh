@@ -43,17 +43,24 @@ __device__ __forceinline__ void warp_pairsum16x2(float* a, float* b, int lane) {
 
 // One CTA tile of the epilogue for one warp (32 rows): MT stacked accumulators of BLOCK_N fp32 columns each at
 // taddr (+ m * BLOCK_N), slice by slice (c outer, m inner).  The tcgen05.ld of the next slice is in flight while
-// the current one is converted; the residual (if any) is register-prefetched one slice ahead.
+// the current one is converted; the residual (if any) is register-prefetched two slices ahead.
 template <int BLOCK_N, int MT>
 __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const bool (&valid)[MT],
                                          const int64_t (&off)[MT], __half* out, const __half* res,
                                          float* sstat_warp /* [BLOCK_N / 2][2] or nullptr */, int lane) {
   constexpr int NCH = BLOCK_N / 32, NIT = NCH * MT;
   uint32_t v[2][32];
-  uint4 rn[4];
-  if (res && valid[0]) {
+  // residual: register-prefetched TWO slices ahead (one ahead left a full L2 / DRAM round trip on every slice)
+  uint4 rn[2][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rn[j] = ldg_nc_v4(res + off[0] + j * 8);
+  for (int pre = 0; pre < 2; ++pre) {
+    if (pre < NIT) {
+      const int pc = pre / MT, pm = pre % MT;
+      if (res && valid[pm]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rn[pre][j] = ldg_nc_v4(res + off[pm] + pc * 32 + j * 8);
+      }
+    }
   }
   tmem_ld_32x32(taddr, v[0]);
   float a1[16], a2[16];
@@ -68,12 +75,12 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
     uint4 rc[4];
     if (res) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rc[j] = rn[j];
-      if (it + 1 < NIT) {
-        const int nc = (it + 1) / MT, nm = (it + 1) % MT;
+      for (int j = 0; j < 4; ++j) rc[j] = rn[it & 1][j];
+      if (it + 2 < NIT) {
+        const int nc = (it + 2) / MT, nm = (it + 2) % MT;
         if (valid[nm]) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rn[j] = ldg_nc_v4(res + off[nm] + nc * 32 + j * 8);
+          for (int j = 0; j < 4; ++j) rn[it & 1][j] = ldg_nc_v4(res + off[nm] + nc * 32 + j * 8);
         }
       }
     }
