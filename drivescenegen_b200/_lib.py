@@ -89,6 +89,7 @@ SIGNATURES = {
     "dsg_conv_in": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_conv_in_scaled": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_conv_in_stats": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dsg_conv_out_fused": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_conv_out": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_gn_stats": (C.c_int, [_p, _i32, _p, _i32, _i64, _p]),
     "dsg_gn_apply": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _p, _p, _f, _i32, _p, _i32, _i64, _i32, _p]),

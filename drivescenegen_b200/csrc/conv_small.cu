@@ -282,6 +282,161 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
   }
 }
 
+// ------------------------------------------------------------------ conv_out on the tensor cores, GroupNorm+SiLU fused
+// conv_norm_out + SiLU + conv_out (64 -> out_channels <= 8) in one pass over the raw 64-channel tensor: a block stages a
+// (8 + 2) x (64 + 2)-pixel window with cp.async, applies y = silu(a_c x + b_c) to it in place (the coefficients of
+// dsg_gn_coef and the arithmetic of gn_apply_kernel: the staged fp16 values are bit-identical to the unfused path), then
+// every warp runs one image row as 4 interleaved m16n8k16 mma.sync tiles: A fragments by ldmatrix.x4 from the window
+// (pixel pitch 144 B: conflict-free), all 36 B fragments (K = 9 taps x 64 channels, N = 8) in 72 registers per thread,
+// NCHW fp32 stores.  The activated tensor is never written to or re-read from HBM (inference only: the training program
+// keeps it for conv_out's weight gradient).
+constexpr int CO_ROWS = 8, CO_TW = 64, CO_WW = CO_TW + 2, CO_PITCH = 144;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __half* __restrict__ x,
+                                                                       const float2* __restrict__ coef,
+                                                                       const float* __restrict__ w,
+                                                                       const float* __restrict__ b,
+                                                                       float* __restrict__ out, int n, int h, int wd,
+                                                                       int cout) {
+  extern __shared__ __align__(16) unsigned char co_smem[];   // [CO_ROWS + 2][CO_WW] pixels x CO_PITCH bytes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  pdl_sync();
+  // B fragments: k-step s = tap * 4 + c16; b0 = W[k = 2t, 2t + 1][n = g], b1 = W[k + 8, k + 9][g]; W[k][n] = w[n][c][tap]
+  uint32_t bf[36][2];
+#pragma unroll
+  for (int s = 0; s < 36; ++s)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int tap = s >> 2, c = (s & 3) * 16 + hh * 8 + 2 * t;
+      const float w0 = g < cout ? w[(g * 64 + c) * 9 + tap] : 0.f;
+      const float w1 = g < cout ? w[(g * 64 + c + 1) * 9 + tap] : 0.f;
+      const __half2 hv = __floats2half2_rn(w0, w1);
+      bf[s][hh] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+  const float bias0 = 2 * t < cout ? b[2 * t] : 0.f, bias1 = 2 * t + 1 < cout ? b[2 * t + 1] : 0.f;
+  // ldmatrix lane address: matrix m = lane / 8 -> pixel rows (lane % 8) + 8 * (m & 1), channel offset 8 * (m >> 1)
+  const uint32_t lm_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * CO_PITCH + (lane >> 4) * 16);
+  const uint32_t win_u32 = smem_u32(co_smem);
+  const int chunk = threadIdx.x & 7, pslot = threadIdx.x >> 3;   // staging: 16-byte channel chunk, pixel slot (32 / pass)
+
+  const int strips = (h + CO_ROWS - 1) / CO_ROWS, ctiles = (wd + CO_TW - 1) / CO_TW;
+  const int64_t items = (int64_t)n * strips * ctiles;
+  const int64_t hw = (int64_t)h * wd;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ct = (int)(item % ctiles);
+    const int64_t r2 = item / ctiles;
+    const int y0 = (int)(r2 % strips) * CO_ROWS, nn = (int)(r2 / strips), x0 = ct * CO_TW;
+    // per-sample GroupNorm coefficients of this thread's 8 channels: (a / 2, b / 2)
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 cf = coef ? coef[(int64_t)nn * 64 + chunk * 8 + j] : make_float2(0.f, 0.f);
+      ca[j] = cf.x; cb[j] = cf.y;
+    }
+    __syncthreads();   // the previous item's window is no longer being read
+    // The thread owns window columns pslot, pslot + 32 (and pslot + 64 for pslot < 2) of every window row, one 16-byte
+    // channel chunk each: addresses advance by constants, the column predicates are computed once per item.
+    constexpr int NCOL = 3;
+    bool col_ok[NCOL];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) {
+      const int c = pslot + 32 * j, xx = x0 - 1 + c;
+      col_ok[j] = c < CO_WW && xx >= 0 && xx < wd;
+    }
+    const __half* gsrc = x + (((int64_t)nn * h + (y0 - 1)) * wd + (x0 - 1 + pslot)) * 64 + chunk * 8;
+    const uint32_t sdst = win_u32 + (uint32_t)(pslot * CO_PITCH + chunk * 16);
+    // stage 1: the raw window straight into shared memory with cp.async — every piece of the thread (up to 30) is in
+    // flight at once: one round trip to L2 / HBM per item; zeros outside the image
+#pragma unroll
+    for (int r = 0; r < CO_ROWS + 2; ++r) {
+      const int yy = y0 - 1 + r;
+      const bool row_ok = yy >= 0 && yy < h;
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        if (pslot + 32 * j >= CO_WW) continue;
+        const uint32_t dst = sdst + (uint32_t)((r * CO_WW + 32 * j) * CO_PITCH);
+        if (row_ok && col_ok[j]) {
+          const __half* src = gsrc + ((int64_t)r * wd + 32 * j) * 64;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        } else {
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // stage 2: GroupNorm + SiLU in place on the pieces this thread fetched (no block barrier needed in between).
+    // Pixels outside the image stay zero: the conv pads the ACTIVATED tensor.
+    if (coef) {
+#pragma unroll
+      for (int r = 0; r < CO_ROWS + 2; ++r) {
+        const int yy = y0 - 1 + r;
+        const bool row_ok = yy >= 0 && yy < h;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+          if (pslot + 32 * j >= CO_WW || !(row_ok && col_ok[j])) continue;
+          const uint32_t a = sdst + (uint32_t)((r * CO_WW + 32 * j) * CO_PITCH);
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // gn_apply_kernel's arithmetic: fp32, rounded once to fp16
+            const float hh = fmaf(f[k], ca[k], cb[k]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+            f[k] = fmaf(hh, th, hh);
+          }
+          v = pack8(f);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+      }
+    }
+    __syncthreads();
+    const int y = y0 + warp;
+    if (y < h) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { acc[i][0] = bias0; acc[i][1] = bias1; acc[i][2] = bias0; acc[i][3] = bias1; }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const uint32_t rowb = win_u32 + (uint32_t)(((warp + ky) * CO_WW + kx) * CO_PITCH) + lm_off;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t af[4];
+            ldmatrix_x4(af, rowb + (uint32_t)(i * 16 * CO_PITCH + c16 * 32));
+            mma_m16n8k16(acc[i], af, bf[tap * 4 + c16][0], bf[tap * 4 + c16][1]);
+          }
+        }
+      }
+      // NCHW fp32: lane (g, t) holds channels 2t, 2t + 1 of pixels x0 + 16 i + g and + 8
+      float* orow = out + ((int64_t)nn * cout * h + y) * wd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int xa = x0 + i * 16 + g, xb = xa + 8;
+        if (2 * t < cout) {
+          if (xa < wd) orow[(int64_t)(2 * t) * hw + xa] = acc[i][0];
+          if (xb < wd) orow[(int64_t)(2 * t) * hw + xb] = acc[i][2];
+        }
+        if (2 * t + 1 < cout) {
+          if (xa < wd) orow[(int64_t)(2 * t + 1) * hw + xa] = acc[i][1];
+          if (xb < wd) orow[(int64_t)(2 * t + 1) * hw + xb] = acc[i][3];
+        }
+      }
+    }
+  }
+}
+
 // warp = 8 adjacent pixels x 4 lanes; each lane owns cin/4 input channels; lanes reduced by shuffle.
 // Weights in smem as [tap][co][cin].
 template <int MAXCO>
@@ -429,6 +584,28 @@ int dsg_conv_in_stats(const float* x, const float* w, const float* b, void* out_
   int rc = dsg_conv_in(x, w, b, out_h16, n, cin, h, wd, cout, stream);
   if (rc != DSG_OK) return rc;
   return dsg_gn_stats(out_h16, cout, stats, n, (int64_t)h * wd, stream);
+}
+
+int dsg_conv_out_fused(const void* x_h16, const float* gn_coef, const float* w, const float* b, float* out, int32_t n,
+                       int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream) {
+  DSG_CHECK_ARG(x_h16 && w && b && out, "dsg_conv_out_fused: null pointer");
+  DSG_CHECK_ARG(cin == 64 && cout >= 1 && cout <= 8, "dsg_conv_out_fused: needs cin == 64 and cout <= 8");
+  DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_out_fused: bad shape");
+  DSG_CHECK_ARG((uintptr_t)x_h16 % 16 == 0 && (uintptr_t)gn_coef % 8 == 0, "dsg_conv_out_fused: unaligned pointer");
+  if (n == 0) return DSG_OK;
+  const size_t sm = (size_t)(CO_ROWS + 2) * CO_WW * CO_PITCH;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) { set_error("dsg_conv_out_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int64_t items = (int64_t)n * ((h + CO_ROWS - 1) / CO_ROWS) * ((wd + CO_TW - 1) / CO_TW);
+  const int64_t blocks = items < 148 * 2 ? items : 148 * 2;
+  launch_k(conv_out_mma_kernel, dim3((unsigned)blocks), dim3(CO_ROWS * 32), sm, (cudaStream_t)stream,
+           (const __half*)x_h16, (const float2*)gn_coef, w, b, out, n, h, wd, cout);
+  DSG_CUDA_LAUNCH_CHECK("dsg_conv_out_fused");
+  return DSG_OK;
 }
 
 int dsg_conv_out(const void* x_h16, const float* w, const float* b, float* out, int32_t n, int32_t cin, int32_t h,

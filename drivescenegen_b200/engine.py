@@ -85,6 +85,7 @@ class UNetEngine:
         # the level-0 tensors of a 16-sample batch are 134 MB each (> the 126 MB L2), those of a 2-4 sample group are
         # not, so running conv -> GroupNorm -> conv ... group by group lets each consumer find its input in L2
         self.l2_group = int(os.environ.get("DSG_L2_GROUP", "0"))
+        self.conv_out_mma = int(os.environ.get("DSG_CONV_OUT_MMA", "1"))   # fused conv_norm_out + SiLU + conv_out
         self.train_packs = False  # also pack the data-gradient forms of every conv weight (training path)
         self.train_programs: Dict[Tuple[int, int, int, int], object] = {}
         self._build_topology()
@@ -434,6 +435,7 @@ class _Program:
             self._regroup(g)
 
     regroup = True   # the training program (engine_train.TrainProgram) keeps whole-batch launches
+    fuse_out_mma = True   # ... and the activated conv_norm_out tensor (conv_out's weight gradient reads it)
 
     def _regroup(self, g: int):
         """Re-issue every run of consecutive full-resolution ops sample-group by sample-group (depth first): all of
@@ -774,13 +776,23 @@ class _Program:
         tc_out = bool("conv_out.w16" in W and tw and hw[0] >= 2 * (128 // tw) + 2 and eng.conv_impl != 1)
         fuse_out = tc_out and self._fusable(hw, c0, c0, 16)
         coef = act = st_out = None
+        meta = {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2), "flops": 2 * b * hw[0] * hw[1] * self.cout * 9 * c0}
+        if self.fuse_out_mma and eng.conv_out_mma and c0 == 64 and self.cout <= 8 and eng.conv_impl != 1:
+            # inference: conv_norm_out + SiLU + conv_out in ONE pass over the raw tensor (warp-level mma.sync kernel)
+            coef = self._gn_coef(x, c0, None, 0, hw, "norm_out.g", "norm_out.b")
+            self._record({"kind": "out", "x": x, "hw": hw, "act": None, "st1": None, "c0": c0})
+            cf_args = (x.data_ptr(), coef.data_ptr(), W["conv_out.w"].data_ptr(), W["conv_out.b"].data_ptr())
+            cf_tail = (b, c0, hw[0], hw[1], self.cout)
+            self._emit("conv_out", meta,
+                       lambda st: check(lib.dsg_conv_out_fused(*cf_args, self.out_ptr, *cf_tail, st), "conv_out (fused)"))
+            self.n_launches = len(self.ops) + 1
+            return
         if fuse_out:
             coef = self._gn_coef(x, c0, None, 0, hw, "norm_out.g", "norm_out.b")
         else:
             act = self._tmp("act", hw, c0)
             st_out, _ = self._gn(x, c0, None, 0, hw, "norm_out.g", "norm_out.b", 1, act)
         self._record({"kind": "out", "x": x, "hw": hw, "act": act, "st1": st_out, "c0": c0})
-        meta = {"bytes": b * hw[0] * hw[1] * (self.cout * 4 + c0 * 2), "flops": 2 * b * hw[0] * hw[1] * self.cout * 9 * c0}
         if tc_out:
             # tcgen05 path: the halo-reuse igemm with BLOCK_N = 16 and an NCHW fp32 epilogue
             a = ConvArgs()

@@ -28,6 +28,7 @@ from .engine import UNetEngine, _Program, _p
 
 class TrainProgram(_Program):
     regroup = False   # whole-batch launches: the backward op list is built against the forward's whole-batch buffers
+    fuse_out_mma = False   # conv_out's weight gradient needs the activated conv_norm_out tensor
 
     def __init__(self, eng: UNetEngine, batch: int, h: int, w: int, grad_slices: Dict[str, torch.Tensor]):
         """grad_slices: parameter name (upstream state-dict key) -> fp32 view that receives its gradient."""

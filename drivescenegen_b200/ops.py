@@ -106,6 +106,19 @@ def conv_out(x_nhwc, w, b):
     return out
 
 
+def conv_out_fused(x_nhwc, coef, w, b):
+    """conv_norm_out + SiLU + conv_out in one pass: x raw fp16 NHWC [n,h,w,64], coef fp32 [n,64,2] from gn_coef (or None
+    when x is already activated) -> fp32 NCHW [n,cout,h,w]."""
+    _cuda(x_nhwc, coef, w, b)
+    lib = _lib.load()
+    n, h, wd, cin = x_nhwc.shape
+    cout = w.shape[0]
+    out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x_nhwc.device)
+    check(lib.dsg_conv_out_fused(x_nhwc.data_ptr(), _p(coef), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, cin, h, wd,
+                                 cout, _st(x_nhwc)), "conv_out_fused")
+    return out
+
+
 def gn_stats(x):
     """Per-channel GroupNorm totals of x fp16 NHWC [n,h,w,c]: int64 [n,c,2] = {sum * 2^24, sum of squares * 2^20}."""
     _cuda(x)

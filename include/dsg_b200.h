@@ -112,6 +112,12 @@ int dsg_conv_in_stats(const float* x, const float* w, const float* b, void* out_
 int dsg_conv_out(const void* x_h16, const float* w, const float* b, float* out, int32_t n, int32_t cin, int32_t h,
                  int32_t wd, int32_t cout, void* stream);
 
+/* conv_norm_out + SiLU + conv_out in one pass (inference): x_h16 is the RAW 64-channel tensor, gn_coef the float2
+ * [n][64] coefficients of dsg_gn_coef ((a/2, b/2) with GroupNorm(x) = a x + b; NULL = x is already activated).
+ * cin == 64, cout <= 8; warp-level mma.sync (fp16 operands, fp32 accumulate), NCHW fp32 output. */
+int dsg_conv_out_fused(const void* x_h16, const float* gn_coef, const float* w, const float* b, float* out, int32_t n,
+                       int32_t cin, int32_t h, int32_t wd, int32_t cout, void* stream);
+
 /* GroupNorm over the channel-concatenation of up to two h16 tensors (x1 has c1 channels, x2 has c2, x2 may be NULL).
  * Statistics are per-channel fixed-point totals: stats int64 [n][c][2] = { sum(x) * 2^24, sum(x^2) * 2^20 },
  * accumulated with integer atomics (order-independent, bit-reproducible).  They come either from dsg_conv's

@@ -202,6 +202,40 @@ def test_conv_in_stats_tensor_core_form_vs_torch(n, cin, cout, h, w):
     assert ((st2[..., 1] - st[..., 1]).abs() / st[..., 1]).max().item() < 2e-3
 
 
+@pytest.mark.parametrize("n,h,w,cout", [(2, 20, 28, 3), (1, 64, 64, 3), (2, 9, 70, 3), (3, 17, 130, 4), (1, 8, 16, 1),
+                                        (4, 256, 256, 3)])
+def test_conv_out_fused_groupnorm_silu_vs_torch(n, h, w, cout):
+    """dsg_conv_out_fused (conv_norm_out + SiLU + conv_out in one mma.sync pass over the raw tensor) against torch fp32
+    group_norm -> silu -> conv2d, and its already-activated form (coef = NULL) against conv2d alone; also against the
+    unfused library path (gn_apply + conv_out), which stages bit-identical fp16 activations."""
+    import torch.nn.functional as F
+    from drivescenegen_b200 import ops
+    torch.manual_seed(4)
+    d = _dev()
+    x = (torch.randn(n, h, w, 64) * 1.5 + 0.3).half()
+    gamma, beta = 1 + 0.2 * torch.randn(64), 0.2 * torch.randn(64)
+    co = torch.nn.Conv2d(64, cout, 3, padding=1)
+    wt, bs = co.weight.detach(), co.bias.detach()
+    xn = x.float().permute(0, 3, 1, 2)
+    with torch.no_grad():
+        act_ref = F.silu(F.group_norm(xn, 32, gamma, beta, 1e-5))
+        ref = F.conv2d(act_ref, wt, bs, padding=1)
+        ref_plain = F.conv2d(xn, wt, bs, padding=1)
+    xd = x.to(d)
+    st = ops.gn_stats(xd)
+    coef = ops.gn_coef(st, None, gamma.to(d), beta.to(d), 32, 1e-5, h * w)
+    got = ops.conv_out_fused(xd, coef, wt.to(d), bs.to(d)).cpu()
+    assert got.shape == ref.shape
+    assert ((got - ref).norm() / ref.norm()).item() < 2e-3
+    assert torch.allclose(got, ref, atol=8e-3, rtol=5e-3), (got - ref).abs().max()
+    got_plain = ops.conv_out_fused(xd, None, wt.to(d), bs.to(d)).cpu()
+    assert ((got_plain - ref_plain).norm() / ref_plain.norm()).item() < 1e-3
+    # the unfused path: same fp16 activations, fp32 weights on CUDA cores -> differs only by weight rounding / sum order
+    act = ops.group_norm(xd, None, gamma.to(d), beta.to(d), 32, 1e-5, 1, stats1=st)
+    unf = ops.conv_out(act, wt.to(d), bs.to(d)).cpu()
+    assert ((got - unf).norm() / unf.norm()).item() < 1e-3
+
+
 @pytest.mark.parametrize("c1,c2,hw", [(64, 0, (32, 32)), (128, 64, (16, 16)), (512, 256, (8, 8)), (256, 128, (12, 20)),
                                       (1024, 0, (8, 8))])
 @pytest.mark.parametrize("act", [0, 1])

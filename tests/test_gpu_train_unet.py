@@ -177,3 +177,36 @@ def test_reference_train_loop_sequence_fused_vs_torch_optimizer(precision):
     assert diff.max().item() < 4e-4, diff.max().item()
     assert (diff > 4e-6).float().mean().item() < 2e-3, (diff > 4e-6).float().mean().item()
     assert l_f[-1] < l_f[0]
+
+
+def test_full_size_training_step_properties_batch32_256():
+    """BASELINE configs[2] at its full size (reference U-Net, 256x256, batch 32), through properties that need no CPU
+    oracle: (1) two identical forward+backward passes give bit-identical gradients (every kernel is deterministic);
+    (2) the gradient of the mean loss over 32 samples is the mean of the gradients of its two 16-sample halves
+    (the backward is linear in the per-sample losses; GroupNorm / attention never mix samples)."""
+    import torch.nn.functional as F
+    from drivescenegen_b200.hostapi import UNet2DModel
+    cfg = dict(CFG_REF, sample_size=256)
+    torch.manual_seed(0)
+    model = UNet2DModel(**cfg).to(_dev()).train()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(32, 3, 256, 256, generator=g).to(_dev())
+    noise = torch.randn(32, 3, 256, 256, generator=g).to(_dev())
+    t = torch.randint(0, 1000, (32,), generator=g).to(_dev())
+
+    def grads(sl):
+        model.zero_grad(set_to_none=True)
+        out = model(x[sl], t[sl], return_dict=False)[0]
+        loss = F.mse_loss(out, noise[sl])
+        loss.backward()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone(), loss.item()
+
+    full1, l1 = grads(slice(0, 32))
+    full2, l2 = grads(slice(0, 32))
+    assert torch.isfinite(full1).all() and full1.abs().max().item() > 0
+    assert l1 == l2 and torch.equal(full1, full2)
+    ga, la = grads(slice(0, 16))
+    gb, lb = grads(slice(16, 32))
+    assert abs(0.5 * (la + lb) - l1) <= 1e-5 * abs(l1)
+    # each half runs with its own power-of-two gradient scale and fp16 roundings: agreement at fp16 resolution
+    assert _rel(0.5 * (ga + gb), full1) < 5e-3

@@ -144,6 +144,10 @@ def test_grad_mode_forward_matches_inference_and_input_grad_raises():
     with torch.no_grad():
         ref = model(x, 1).sample
     out = model(x, 1).sample
-    assert out.requires_grad and torch.equal(out.detach(), ref)
+    # same arithmetic up to conv_out: inference fuses conv_norm_out + SiLU + conv_out into one mma.sync pass (fp16
+    # weights), the training program keeps the activated tensor and runs the tcgen05 conv_out
+    assert out.requires_grad
+    assert ((out.detach() - ref).norm() / ref.norm()).item() < 1e-3
+    assert torch.allclose(out.detach(), ref, atol=2e-3, rtol=2e-3)
     with pytest.raises(NotImplementedError):
         model(x.clone().requires_grad_(True), 1)
