@@ -284,13 +284,14 @@ __global__ void __launch_bounds__(CM_ROWS * 32, 2) conv_in_mma_kernel(const floa
 
 // ------------------------------------------------------------------ conv_out on the tensor cores, GroupNorm+SiLU fused
 // conv_norm_out + SiLU + conv_out (64 -> out_channels <= 8) in one pass over the raw 64-channel tensor: a block stages a
-// (8 + 2) x (64 + 2)-pixel window with cp.async, applies y = silu(a_c x + b_c) to it in place (the coefficients of
+// (8 + 2) x (32 + 2)-pixel window with cp.async (double-buffered: the next window is in flight while this one is worked on), applies y = silu(a_c x + b_c) to it in place (the coefficients of
 // dsg_gn_coef and the arithmetic of gn_apply_kernel: the staged fp16 values are bit-identical to the unfused path), then
-// every warp runs one image row as 4 interleaved m16n8k16 mma.sync tiles: A fragments by ldmatrix.x4 from the window
+// every warp runs one image row as 2 interleaved m16n8k16 mma.sync tiles: A fragments by ldmatrix.x4 from the window
 // (pixel pitch 144 B: conflict-free), all 36 B fragments (K = 9 taps x 64 channels, N = 8) in 72 registers per thread,
 // NCHW fp32 stores.  The activated tensor is never written to or re-read from HBM (inference only: the training program
 // keeps it for conv_out's weight gradient).
-constexpr int CO_ROWS = 8, CO_TW = 64, CO_WW = CO_TW + 2, CO_PITCH = 144;
+constexpr int CO_ROWS = 8, CO_TW = 32, CO_WW = CO_TW + 2, CO_PITCH = 144;
+constexpr int CO_WIN_BYTES = (CO_ROWS + 2) * CO_WW * CO_PITCH;   // one window; the kernel keeps two
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __h
                                                                        const float* __restrict__ b,
                                                                        float* __restrict__ out, int n, int h, int wd,
                                                                        int cout) {
-  extern __shared__ __align__(16) unsigned char co_smem[];   // [CO_ROWS + 2][CO_WW] pixels x CO_PITCH bytes
+  extern __shared__ __align__(16) unsigned char co_smem[];   // 2 x [CO_ROWS + 2][CO_WW] pixels x CO_PITCH bytes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   pdl_sync();
@@ -324,12 +325,47 @@ __global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __h
   // ldmatrix lane address: matrix m = lane / 8 -> pixel rows (lane % 8) + 8 * (m & 1), channel offset 8 * (m >> 1)
   const uint32_t lm_off = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * CO_PITCH + (lane >> 4) * 16);
   const uint32_t win_u32 = smem_u32(co_smem);
-  const int chunk = threadIdx.x & 7, pslot = threadIdx.x >> 3;   // staging: 16-byte channel chunk, pixel slot (32 / pass)
+  // staging: the thread owns one 16-byte channel chunk of window pixels pslot, pslot + 32, ... (an even deal: a
+  // column-wise ownership left the two threads of the 2-pixel halo with twice the work and everyone else at the barrier)
+  const int chunk = threadIdx.x & 7, pslot = threadIdx.x >> 3;
+  constexpr int NPX = (CO_ROWS + 2) * CO_WW, NPIECE = (NPX + 31) / 32;
 
   const int strips = (h + CO_ROWS - 1) / CO_ROWS, ctiles = (wd + CO_TW - 1) / CO_TW;
   const int64_t items = (int64_t)n * strips * ctiles;
   const int64_t hw = (int64_t)h * wd;
-  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+
+  // the raw window of `item` into buffer `buf` with cp.async (zeros outside the image), one commit group per call
+  auto issue = [&](int64_t item, int buf) {
+    if (item < items) {
+      const int ct = (int)(item % ctiles);
+      const int64_t r2 = item / ctiles;
+      const int y0 = (int)(r2 % strips) * CO_ROWS, nn = (int)(r2 / strips), x0 = ct * CO_TW;
+      const __half* gsrc = x + (((int64_t)nn * h + (y0 - 1)) * wd + (x0 - 1)) * 64 + chunk * 8;
+      const uint32_t sdst = win_u32 + (uint32_t)(buf * CO_WIN_BYTES) + (uint32_t)(chunk * 16);
+#pragma unroll
+      for (int k = 0; k < NPIECE; ++k) {
+        const int p = pslot + 32 * k;        // window pixel: pieces are dealt round-robin, every thread gets 10 or 11
+        if (p >= NPX) break;
+        const int r = p / CO_WW, c = p - r * CO_WW;
+        const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+        const uint32_t dst = sdst + (uint32_t)(p * CO_PITCH);
+        if (yy >= 0 && yy < h && xx >= 0 && xx < wd) {
+          const __half* src = gsrc + ((int64_t)r * wd + c) * 64;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        } else {
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  issue(blockIdx.x, 0);
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
+    // the window of the NEXT item is fetched while this one is transformed and multiplied: its buffer was last read in
+    // the previous iteration, which ended with a block barrier
+    issue(item + gridDim.x, buf ^ 1);
     const int ct = (int)(item % ctiles);
     const int64_t r2 = item / ctiles;
     const int y0 = (int)(r2 % strips) * CO_ROWS, nn = (int)(r2 / strips), x0 = ct * CO_TW;
@@ -340,79 +376,49 @@ __global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __h
       const float2 cf = coef ? coef[(int64_t)nn * 64 + chunk * 8 + j] : make_float2(0.f, 0.f);
       ca[j] = cf.x; cb[j] = cf.y;
     }
-    __syncthreads();   // the previous item's window is no longer being read
-    // The thread owns window columns pslot, pslot + 32 (and pslot + 64 for pslot < 2) of every window row, one 16-byte
-    // channel chunk each: addresses advance by constants, the column predicates are computed once per item.
-    constexpr int NCOL = 3;
-    bool col_ok[NCOL];
-#pragma unroll
-    for (int j = 0; j < NCOL; ++j) {
-      const int c = pslot + 32 * j, xx = x0 - 1 + c;
-      col_ok[j] = c < CO_WW && xx >= 0 && xx < wd;
-    }
-    const __half* gsrc = x + (((int64_t)nn * h + (y0 - 1)) * wd + (x0 - 1 + pslot)) * 64 + chunk * 8;
-    const uint32_t sdst = win_u32 + (uint32_t)(pslot * CO_PITCH + chunk * 16);
-    // stage 1: the raw window straight into shared memory with cp.async — every piece of the thread (up to 30) is in
-    // flight at once: one round trip to L2 / HBM per item; zeros outside the image
-#pragma unroll
-    for (int r = 0; r < CO_ROWS + 2; ++r) {
-      const int yy = y0 - 1 + r;
-      const bool row_ok = yy >= 0 && yy < h;
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) {
-        if (pslot + 32 * j >= CO_WW) continue;
-        const uint32_t dst = sdst + (uint32_t)((r * CO_WW + 32 * j) * CO_PITCH);
-        if (row_ok && col_ok[j]) {
-          const __half* src = gsrc + ((int64_t)r * wd + 32 * j) * 64;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        } else {
-          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // stage 2: GroupNorm + SiLU in place on the pieces this thread fetched (no block barrier needed in between).
-    // Pixels outside the image stay zero: the conv pads the ACTIVATED tensor.
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the group just committed has landed
+    // GroupNorm + SiLU in place on the pieces this thread fetched (no block barrier needed in between).  Pixels outside
+    // the image stay zero: the conv pads the ACTIVATED tensor.
+    const uint32_t wbase = win_u32 + (uint32_t)(buf * CO_WIN_BYTES);
     if (coef) {
 #pragma unroll
-      for (int r = 0; r < CO_ROWS + 2; ++r) {
-        const int yy = y0 - 1 + r;
-        const bool row_ok = yy >= 0 && yy < h;
+      for (int k = 0; k < NPIECE; ++k) {
+        const int p = pslot + 32 * k;
+        if (p >= NPX) break;
+        const int r = p / CO_WW, c = p - r * CO_WW;
+        const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+        if (yy < 0 || yy >= h || xx < 0 || xx >= wd) continue;
+        const uint32_t a = wbase + (uint32_t)(p * CO_PITCH + chunk * 16);
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        float f[8];
+        unpack8(v, f);
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) {
-          if (pslot + 32 * j >= CO_WW || !(row_ok && col_ok[j])) continue;
-          const uint32_t a = sdst + (uint32_t)((r * CO_WW + 32 * j) * CO_PITCH);
-          uint4 v;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-          float f[8];
-          unpack8(v, f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {   // gn_apply_kernel's arithmetic: fp32, rounded once to fp16
-            const float hh = fmaf(f[k], ca[k], cb[k]);
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
-            f[k] = fmaf(hh, th, hh);
-          }
-          v = pack8(f);
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        for (int kk = 0; kk < 8; ++kk) {   // gn_apply_kernel's arithmetic: fp32, rounded once to fp16
+          const float hh = fmaf(f[kk], ca[kk], cb[kk]);
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+          f[kk] = fmaf(hh, th, hh);
         }
+        v = pack8(f);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
       }
     }
     __syncthreads();
     const int y = y0 + warp;
     if (y < h) {
-      float acc[4][4];
+      constexpr int NT = CO_TW / 16;
+      float acc[NT][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[i][0] = bias0; acc[i][1] = bias1; acc[i][2] = bias0; acc[i][3] = bias1; }
+      for (int i = 0; i < NT; ++i) { acc[i][0] = bias0; acc[i][1] = bias1; acc[i][2] = bias0; acc[i][3] = bias1; }
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int ky = tap / 3, kx = tap - ky * 3;
-        const uint32_t rowb = win_u32 + (uint32_t)(((warp + ky) * CO_WW + kx) * CO_PITCH) + lm_off;
+        const uint32_t rowb = wbase + (uint32_t)(((warp + ky) * CO_WW + kx) * CO_PITCH) + lm_off;
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < NT; ++i) {
             uint32_t af[4];
             ldmatrix_x4(af, rowb + (uint32_t)(i * 16 * CO_PITCH + c16 * 32));
             mma_m16n8k16(acc[i], af, bf[tap * 4 + c16][0], bf[tap * 4 + c16][1]);
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __h
       // NCHW fp32: lane (g, t) holds channels 2t, 2t + 1 of pixels x0 + 16 i + g and + 8
       float* orow = out + ((int64_t)nn * cout * h + y) * wd;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NT; ++i) {
         const int xa = x0 + i * 16 + g, xb = xa + 8;
         if (2 * t < cout) {
           if (xa < wd) orow[(int64_t)(2 * t) * hw + xa] = acc[i][0];
@@ -434,7 +440,9 @@ __global__ void __launch_bounds__(CO_ROWS * 32, 2) conv_out_mma_kernel(const __h
         }
       }
     }
+    __syncthreads();   // every warp is done with this window before the next iteration refills it
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // warp = 8 adjacent pixels x 4 lanes; each lane owns cin/4 input channels; lanes reduced by shuffle.
@@ -593,7 +601,7 @@ int dsg_conv_out_fused(const void* x_h16, const float* gn_coef, const float* w, 
   DSG_CHECK_ARG(n >= 0 && h > 0 && wd > 0, "dsg_conv_out_fused: bad shape");
   DSG_CHECK_ARG((uintptr_t)x_h16 % 16 == 0 && (uintptr_t)gn_coef % 8 == 0, "dsg_conv_out_fused: unaligned pointer");
   if (n == 0) return DSG_OK;
-  const size_t sm = (size_t)(CO_ROWS + 2) * CO_WW * CO_PITCH;
+  const size_t sm = (size_t)2 * CO_WIN_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
