@@ -70,6 +70,20 @@ class PackJob(C.Structure):
     ]
 
 
+class ReduceJob(C.Structure):
+    """mirror of ``dsg_reduce_job`` (include/dsg_b200.h)."""
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("n", C.c_int32), ("parts", C.c_int32), ("c", C.c_int32), ("comps", C.c_int32),
+        ("sample_stride", C.c_int64), ("part_stride", C.c_int64),
+        ("per_n", C.c_void_p),
+        ("per_n_stride", C.c_int32), ("per_n_off", C.c_int32),
+        ("inv_scale", C.c_void_p),
+        ("out0", C.c_void_p), ("out0b", C.c_void_p), ("out1", C.c_void_p),
+        ("block_begin", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
 _i32, _i64, _p, _f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/dsg_b200.h declares (tests check this)
@@ -115,6 +129,7 @@ SIGNATURES = {
     "dsg_gn_bwd_params": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "dsg_colsum_h16": (C.c_int, [_p, _i64, _i32, _p, _i32, _p]),
     "dsg_colsum_finalize": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p]),
+    "dsg_reduce_rows_batched": (C.c_int, [_p, _i32, _i32, _p]),
     "dsg_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), _p]),
     "dsg_wgrad_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "dsg_conv_out_dgrad_weight": (C.c_int, [_p, _i32, _i32, _p, _p, _p]),

@@ -325,6 +325,30 @@ __global__ void __launch_bounds__(GB_THREADS) colsum_h16_kernel(const __half* __
   }
 }
 
+// Every finaliser of one backward pass (d gamma / d beta of each GroupNorm, bias / time-embedding column sums) in ONE
+// launch from a device-side job table: ~100 launches of 10 us each otherwise.  Same body, same fixed order.
+__global__ void __launch_bounds__(256) reduce_rows_batched_kernel(const dsg_reduce_job* __restrict__ jobs, int njobs) {
+  __shared__ float smem_f[RR_SMEM_FLOATS];
+  __shared__ int s_job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;   // last job whose first block is <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    s_job = lo;
+  }
+  __syncthreads();
+  const dsg_reduce_job j = jobs[s_job];
+  const int bx = (int)blockIdx.x - j.block_begin;
+  if (j.comps == 2)
+    reduce_rows_body<2>(j.src, j.n, j.parts, j.c, j.sample_stride, j.part_stride, j.per_n, j.per_n_stride, j.per_n_off,
+                        j.inv_scale, j.out0, j.out0b, j.out1, bx, smem_f);
+  else
+    reduce_rows_body<1>(j.src, j.n, j.parts, j.c, j.sample_stride, j.part_stride, j.per_n, j.per_n_stride, j.per_n_off,
+                        j.inv_scale, j.out0, j.out0b, j.out1, bx, smem_f);
+}
+
 }  // namespace dsg
 
 using namespace dsg;
@@ -387,6 +411,13 @@ int dsg_gn_bwd_params(const float* partial, int32_t n, int32_t chunks, int32_t c
            partial + (int64_t)chunks * c * 2, n, 1, c, (int64_t)(chunks + 1) * c * 2, (int64_t)0, (float*)nullptr, 0, 0,
            inv_scale, dbeta, (float*)nullptr, dgamma);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd_params");
+  return DSG_OK;
+}
+
+int dsg_reduce_rows_batched(const dsg_reduce_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
+  DSG_CHECK_ARG(jobs_dev && njobs >= 1 && total_blocks >= 1, "dsg_reduce_rows_batched: bad args");
+  reduce_rows_batched_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+  DSG_CUDA_LAUNCH_CHECK("dsg_reduce_rows_batched");
   return DSG_OK;
 }
 

@@ -10,18 +10,17 @@ namespace dsg {
 // Block = 32 channels x 8 slices; a slice owns the parts k = slice, slice + 8, ...; all loads of a round are
 // independent (the naive one-thread-per-channel loop was a chain of n * parts dependent L2 latencies).
 template <int COMPS>
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ src, int n, int parts, int C,
-                                                          int64_t sample_stride, int64_t part_stride,
-                                                          float* __restrict__ per_n, int per_n_stride, int per_n_off,
-                                                          const float* __restrict__ inv_scale, float* __restrict__ out0,
-                                                          float* __restrict__ out0b, float* __restrict__ out1) {
+__device__ __forceinline__ void reduce_rows_body(const float* __restrict__ src, int n, int parts, int C,
+                                                 int64_t sample_stride, int64_t part_stride, float* __restrict__ per_n,
+                                                 int per_n_stride, int per_n_off, const float* __restrict__ inv_scale,
+                                                 float* __restrict__ out0, float* __restrict__ out0b,
+                                                 float* __restrict__ out1, int block_x, float* smem_f) {
   constexpr int S = 8, TS = 8;  // slices, samples per round
-  __shared__ float s1[TS][S][32][COMPS];
-  __shared__ float s2[TS][32][COMPS];
+  float (*s1)[S][32][COMPS] = reinterpret_cast<float (*)[S][32][COMPS]>(smem_f);
+  float (*s2)[32][COMPS] = reinterpret_cast<float (*)[32][COMPS]>(smem_f + TS * S * 32 * COMPS);
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
+  const int c = block_x * 32 + lane;
   const bool ok = c < C;
-  pdl_sync();
   float tot[COMPS];
 #pragma unroll
   for (int q = 0; q < COMPS; ++q) tot[q] = 0.f;
@@ -73,6 +72,20 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
     if (out0b) out0b[c] = tot[0] * sc;
     if (COMPS > 1 && out1) out1[c] = tot[COMPS - 1] * sc;
   }
+}
+
+constexpr int RR_SMEM_FLOATS = 2 * (8 * 8 * 32 + 8 * 32);   // s1 + s2 at COMPS = 2
+
+template <int COMPS>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ src, int n, int parts, int C,
+                                                          int64_t sample_stride, int64_t part_stride,
+                                                          float* __restrict__ per_n, int per_n_stride, int per_n_off,
+                                                          const float* __restrict__ inv_scale, float* __restrict__ out0,
+                                                          float* __restrict__ out0b, float* __restrict__ out1) {
+  __shared__ float smem_f[RR_SMEM_FLOATS];
+  pdl_sync();
+  reduce_rows_body<COMPS>(src, n, parts, C, sample_stride, part_stride, per_n, per_n_stride, per_n_off, inv_scale, out0,
+                          out0b, out1, (int)blockIdx.x, smem_f);
 }
 
 }  // namespace dsg

@@ -122,20 +122,23 @@ class TrainProgram(_Program):
         return self._gbuf[key]
 
     # ---- op helpers (each appends to bwd_ops; in the sizing pass buffers may be None and nothing is emitted)
-    def _colsum_to(self, x: torch.Tensor, rows: int, c: int, total, total2=None, scaled=True):
+    def _colsum_to(self, x: torch.Tensor, rows: int, c: int, total, total2=None, scaled=True, split=None):
+        """column sums of x [rows][c] -> total (and total2); split = [(tensor, first column, width), ...] sends column
+        ranges to different destinations instead (the fused q/k/v bias gradient)."""
         lib = self.lib
         parts = max(1, min(148 * 4, -(-rows // 64)))
-        partial = self._btmp("colsum_partial", parts * c, torch.float32)
+        partial = self._btmp(self._uniq("colsum_partial"), parts * c, torch.float32)
         if self._sizing:
             return
         inv = self.inv_scale_ptr if scaled else None
         a1 = (x.data_ptr(), rows, c, partial.data_ptr(), parts)
-        a2 = (partial.data_ptr(), 1, parts, c, None, 0, 0, inv, _p(total), _p(total2))
-
-        def run(st):
-            check(lib.dsg_colsum_h16(*a1, st), "colsum_h16")
-            check(lib.dsg_colsum_finalize(*a2, st), "colsum_finalize")
-        self._bemit("colsum", {"bytes": rows * c * 2}, run)
+        if split is None:
+            self._colsum_job(partial.data_ptr(), 1, parts, c, None, 0, 0, inv, _p(total), _p(total2))
+        else:
+            for dst, col0, width in split:
+                self._rjobs.append(dict(src=partial.data_ptr() + col0 * 4, n=1, parts=parts, c=width, comps=1,
+                                        sample_stride=parts * c, part_stride=c, inv_scale=inv, out0=dst.data_ptr()))
+        self._bemit("colsum", {"bytes": rows * c * 2}, lambda st: check(lib.dsg_colsum_h16(*a1, st), "colsum_h16"))
 
     def _bias_grad(self, t: torch.Tensor, g: torch.Tensor, rows: int, c: int, total, total2=None):
         """bias gradient of the block that produced activation t = column sums of t's complete gradient g: taken from
@@ -144,9 +147,8 @@ class TrainProgram(_Program):
         if rec is None:
             return self._colsum_to(g, rows, c, total, total2)
         buf, parts = rec
-        lib = self.lib
-        a = (buf.data_ptr(), self.b, parts, c, None, 0, 0, self.inv_scale_ptr, _p(total), _p(total2))
-        self._bemit("colsum_finalize", {}, lambda st: check(lib.dsg_colsum_finalize(*a, st), "colsum_finalize"))
+        self._uniq("colsum_partial")   # keep the scratch numbering of the sizing pass (which always took the other path)
+        self._colsum_job(buf.data_ptr(), self.b, parts, c, None, 0, 0, self.inv_scale_ptr, _p(total), _p(total2))
 
     def _wgrad(self, mode, x, dy, hw, cin, cout, grad, ci_total=None, ci_off=0):
         lib = self.lib
@@ -191,9 +193,9 @@ class TrainProgram(_Program):
         eng, lib, b = self.eng, self.lib, self.b
         c, npx = c1 + c2, hw[0] * hw[1]
         chunks = max(1, min(64, (148 * 4) // b, -(-npx // 64)))
-        partial = self._btmp("gn_partial", b * (chunks + 1) * c * 2, torch.float32)
+        partial = self._btmp(self._uniq("gn_partial"), b * (chunks + 1) * c * 2, torch.float32)
         parts = max(1, min((148 * 4) // b, -(-npx // 32))) if (colsum_to or last1 or last2) else 0
-        colsum = self._btmp("gn_colsum", max(1, b * parts * c), torch.float32) if colsum_to else None
+        colsum = self._btmp(self._uniq("gn_colsum"), max(1, b * parts * c), torch.float32) if colsum_to else None
         if self._sizing:
             return
         osum = [None, None]
@@ -207,19 +209,17 @@ class TrainProgram(_Program):
         a1 = (dy.data_ptr(), x1.data_ptr(), c1, st1.data_ptr(), _p(x2), c2, _p(st2), g.data_ptr(), bt.data_ptr(), eng.eps,
               act, partial.data_ptr(), chunks, _p(addend), dx1.data_ptr(), int(acc1), _p(dx2), int(acc2), _p(colsum),
               _p(osum[0]), _p(osum[1]), parts, b, npx, eng.groups)
-        a2 = (partial.data_ptr(), b, chunks, c, self.inv_scale_ptr, g_gamma.data_ptr(), g_beta.data_ptr())
-        a3 = None
+        # d gamma / d beta: per-sample (sum g, sum g * xh) rows left in slot `chunks` of every sample by the apply kernel
+        self._rjobs.append(dict(src=partial.data_ptr() + chunks * c * 2 * 4, n=b, parts=1, c=c, comps=2,
+                                sample_stride=(chunks + 1) * c * 2, part_stride=0, inv_scale=self.inv_scale_ptr,
+                                out0=g_beta.data_ptr(), out1=g_gamma.data_ptr()))
         if colsum_to:
             per_n, stride, off, total = colsum_to
-            a3 = (colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr, _p(total), None)
-
-        def run(st):
-            check(lib.dsg_gn_bwd(*a1, st), "gn_bwd")
-            check(lib.dsg_gn_bwd_params(*a2, st), "gn_bwd_params")
-            if a3 is not None:
-                check(lib.dsg_colsum_finalize(*a3, st), "colsum_finalize")
+            self._colsum_job(colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr,
+                             _p(total), None)
         nbytes = b * npx * c * 2
-        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0)}, run)
+        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0)},
+                    lambda st: check(lib.dsg_gn_bwd(*a1, st), "gn_bwd"))
 
     # ------------------------------------------------------------------ the backward program
     def _emit_backward(self):
@@ -233,9 +233,44 @@ class TrainProgram(_Program):
         self.scale_ptr = self.scale.data_ptr()
         self.inv_scale_ptr = self.scale.data_ptr() + 4
         self.dtemb = eng.arena.get(f"train/{b}/dtemb", b * eng.proj_total, torch.float32)
+        # finalisers (d gamma / d beta, bias / time-embedding column sums) are collected and run as ONE launch at the
+        # end; their inputs therefore live in per-call scratch buffers instead of shared ones
+        self._rjobs: List[dict] = []
+        self._ruid = 0
         for rec in reversed(self.records):
             getattr(self, "_bwd_" + rec["kind"])(rec)
+        self._emit_reduce_jobs()
         self._bwd_time_embed()
+
+    def _uniq(self, name: str) -> str:
+        self._ruid += 1
+        return f"{name}#{self._ruid}"
+
+    def _emit_reduce_jobs(self):
+        if self._sizing or not self._rjobs:
+            return
+        from ._lib import ReduceJob
+        arr = (ReduceJob * len(self._rjobs))()
+        blk = 0
+        for i, j in enumerate(self._rjobs):
+            r = arr[i]
+            r.src, r.n, r.parts, r.c, r.comps = j["src"], j["n"], j["parts"], j["c"], j["comps"]
+            r.sample_stride, r.part_stride = j["sample_stride"], j["part_stride"]
+            r.per_n, r.per_n_stride, r.per_n_off = j.get("per_n"), j.get("per_n_stride", 0), j.get("per_n_off", 0)
+            r.inv_scale, r.out0, r.out0b, r.out1 = j.get("inv_scale"), j.get("out0"), j.get("out0b"), j.get("out1")
+            r.block_begin = blk
+            blk += (j["c"] + 31) // 32
+        raw = bytes(arr)
+        dev = self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/reduce_jobs", len(raw), torch.uint8)
+        dev.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        lib, njobs, total = self.lib, len(self._rjobs), blk
+        ptr = dev.data_ptr()
+        self._bemit("colsum_finalize", {"jobs": njobs},
+                    lambda st: check(lib.dsg_reduce_rows_batched(ptr, njobs, total, st), "reduce_rows_batched"))
+
+    def _colsum_job(self, src: int, n: int, parts: int, c: int, per_n, stride, off, inv, total, total2):
+        self._rjobs.append(dict(src=src, n=n, parts=parts, c=c, comps=1, sample_stride=parts * c, part_stride=c,
+                                per_n=per_n, per_n_stride=stride, per_n_off=off, inv_scale=inv, out0=total, out0b=total2))
 
     def _bwd_out(self, rec):
         """conv_norm_out + SiLU + conv_out; entry point of the backward (sets the gradient scale)."""
@@ -352,17 +387,16 @@ class TrainProgram(_Program):
             self._bemit("attention_bwd", {"flops": 10 * b * npx * npx * ch},
                         lambda st: check(lib.dsg_attention_bwd(*args, st), "attention_bwd"))
         # q/k/v projections: the fused [3c] gradient is scattered to the three parameter pairs
-        qkv_b = self._btmp("attn_qkv_bias", 3 * ch, torch.float32)
         qkv_w = self._btmp("attn_qkv_w", 3 * ch * ch, torch.float32)
-        self._colsum_to(dqkv, b * npx, 3 * ch, qkv_b)
+        self._colsum_to(dqkv, b * npx, 3 * ch, None,
+                        split=[(G[f"{pre}.to_{n}.bias"], i * ch, ch) for i, n in enumerate("qkv")])
         self._wgrad(3, rec["act"], dqkv, hw, ch, 3 * ch, qkv_w)
         if not self._sizing:
-            dst = [(G[f"{pre}.to_{n}.weight"], G[f"{pre}.to_{n}.bias"]) for n in "qkv"]
+            dst = [G[f"{pre}.to_{n}.weight"] for n in "qkv"]
 
             def scatter(st):
-                for i, (gw, gb) in enumerate(dst):
+                for i, gw in enumerate(dst):
                     gw.view(-1).copy_(qkv_w[i * ch * ch:(i + 1) * ch * ch])
-                    gb.copy_(qkv_b[i * ch:(i + 1) * ch])
             self._bemit("qkv_scatter", {}, scatter)
         da = self._btmp("dact", b * npx * ch)
         self._dgrad(3, dqkv, hw, 3 * ch, ch, f"{pre}.qkv.dg", da, flops_k=2 * b * npx * 3 * ch * ch)

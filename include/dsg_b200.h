@@ -324,6 +324,25 @@ int dsg_attention_train(const void* qkv, void* out, float* lse, int32_t n, int32
 int dsg_attention_bwd(const void* qkv, const void* out, const void* dout, void* dqkv, float* ws, const float* lse,
                       int32_t n, int32_t tokens, int32_t heads, int32_t head_dim, void* stream);
 
+/* All finalisers of one backward pass in one launch.  A job is one dsg_gn_bwd_params (comps = 2: src = partial +
+ * chunks * c * 2, parts = 1, sample_stride = (chunks + 1) * c * 2, part_stride = 0, out0 = d beta, out1 = d gamma) or one
+ * dsg_colsum_finalize (comps = 1: src = partial, sample_stride = parts * c, part_stride = c, out0 / out0b = totals,
+ * per_n = optional per-sample sums); block_begin = first block of the job in the flat grid, ceil(c / 32) blocks each,
+ * jobs sorted by block_begin.  Same arithmetic and order as the single calls (bit-identical results). */
+typedef struct dsg_reduce_job {
+  const float* src;
+  int32_t n, parts, c, comps;
+  int64_t sample_stride, part_stride;
+  float* per_n;
+  int32_t per_n_stride, per_n_off;
+  const float* inv_scale;
+  float* out0;
+  float* out0b;
+  float* out1;
+  int32_t block_begin, pad_;
+} dsg_reduce_job;
+int dsg_reduce_rows_batched(const dsg_reduce_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
+
 /* Global gradient norm over one flat fp32 buffer: out3 = { ||g|| * inv_loss_scale, coefficient that unscales and clips
  * (inv_loss_scale * min(1, max_norm / (norm + 1e-6)); max_norm <= 0 disables clipping), 1 if the norm is inf/nan }.
  * partial: double[parts] scratch.  Deterministic (fixed-order sums). */
