@@ -170,6 +170,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
     const int row = q * 32 + lane;
     const int te = threadIdx.x - 64;
     int acc = 0; uint32_t acc_ph = 0;
+    EpiStatsAcc<BLOCK_N> stats_acc;
+    stats_acc.init();
     for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
       const int n0 = tc.nb * BLOCK_N;
@@ -194,10 +196,11 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        epi_stats_flush<BLOCK_N>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
+        stats_acc.add_tile(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
       }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
+    stats_acc.emit(te);
   }
 
   tc_fence_before();

@@ -125,16 +125,46 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
   }
 }
 
-// combine the four warps' pair totals (fixed order) and add them to the tensor's int64 totals
+// combine the four warps' pair totals of one tile (fixed order), convert to the exact fixed-point form and keep them in
+// registers (entry idx is always handled by the same thread); the int64 atomics on the tensor's totals are issued only
+// when the CTA moves on to another (sample, channel block) or runs out of tiles.  Integer adds: the totals are bit-identical
+// to flushing every tile, whatever tiles a CTA happens to process.
 template <int BLOCK_N>
-__device__ __forceinline__ void epi_stats_flush(const float* sstat /* [4][BLOCK_N / 2][2] */, int te /* 0..127 */,
-                                                long long* stats_nc /* &stats[(n * cout + n0) * 2] */) {
-  for (int idx = te; idx < BLOCK_N; idx += 128) {
-    const float v = ((sstat[idx] + sstat[BLOCK_N + idx]) + sstat[2 * BLOCK_N + idx]) + sstat[3 * BLOCK_N + idx];
-    const long long fx = (idx & 1) ? gn_fix_sq(v) : gn_fix_sum(v);
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats_nc + (idx >> 1) * 4 + (idx & 1)), (unsigned long long)fx);
+struct EpiStatsAcc {
+  static constexpr int NV = (BLOCK_N + 127) / 128;
+  long long v[NV];
+  long long* dst;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = 0;
+    dst = nullptr;
   }
-}
+  __device__ __forceinline__ void emit(int te) {
+    if (dst != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int idx = te + k * 128;
+        if (idx < BLOCK_N && v[k] != 0)
+          atomicAdd(reinterpret_cast<unsigned long long*>(dst + (idx >> 1) * 4 + (idx & 1)), (unsigned long long)v[k]);
+        v[k] = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void add_tile(const float* sstat /* [4][BLOCK_N / 2][2] */, int te, long long* stats_nc) {
+    if (stats_nc != dst) {
+      emit(te);
+      dst = stats_nc;
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int idx = te + k * 128;
+      if (idx < BLOCK_N) {
+        const float t = ((sstat[idx] + sstat[BLOCK_N + idx]) + sstat[2 * BLOCK_N + idx]) + sstat[3 * BLOCK_N + idx];
+        v[k] += (idx & 1) ? gn_fix_sq(t) : gn_fix_sum(t);
+      }
+    }
+  }
+};
 
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -412,6 +412,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     const int te = threadIdx.x - 64;
     const int lh0 = row >> p.tw_shift, lw = row & (p.TW - 1);
     int acc = 0; uint32_t acc_ph = 0;
+    EpiStatsAcc<BLOCK_N> stats_acc;
+    stats_acc.init();
     for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
       const HlTile tc = hl_decode(p, t, CG, (int)rank);
       const int n0 = tc.nb * BLOCK_N;
@@ -476,10 +478,11 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
       }
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        epi_stats_flush<BLOCK_N>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
+        stats_acc.add_tile(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
       }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
+    stats_acc.emit(te);
   }
 
   tc_fence_before();
