@@ -11,7 +11,8 @@ samples with random-init weights of the reference architecture (DriveSceneGen/sc
             pinned host memory to the device and reads the new sample back to pinned host memory; the copies run
             on their own streams beside the next step's compute (serial copy->step->copy->sync time also reported).
   roofline  the tcgen05 implicit-GEMM conv kernel: algorithmic conv/linear FLOPs of one step (reference op count)
-            / summed CUDA-event duration of those launches in an eager, per-launch-timed replay of the same step.
+            / summed CUDA-event duration of those launches in an eager, per-launch-timed replay of the same step
+            (per-launch median of 5 replays).
   cpu_baseline / --impl reference: the CPU oracle (plain PyTorch fp32 restatement of the reference path) on this
             box's host cores, bounded sample (batch 2).
 Prints ONE JSON line on rank 0.
@@ -102,6 +103,16 @@ def use_all_host_threads() -> int:
     if torch.get_num_threads() != n:
         torch.set_num_threads(n)
     return torch.get_num_threads()
+
+
+def median_table(tables):
+    """per-launch median over several event-timed eager replays of the same op list: one replay is exposed to single
+    multi-millisecond outliers (a host hiccup between two launches lands in one launch's event pair)."""
+    out = []
+    for rows in zip(*tables):
+        ms = sorted(r[2] for r in rows)
+        out.append((rows[0][0], rows[0][1], ms[len(ms) // 2]))
+    return out
 
 
 def oracle_steps_per_s(batch: int, size: int, steps: int, warmup: int):
@@ -274,8 +285,8 @@ def run_train(args):
     dout = torch.randn(B, 3, S, S, device=dev) * 1e-3
     prog.run(noisy, tf)
     prog.backward_timed(dout, noisy)
-    fwd = prog.run_timed(noisy, tf)
-    bwd = prog.backward_timed(dout, noisy)
+    fwd = median_table([prog.run_timed(noisy, tf) for _ in range(3)])
+    bwd = median_table([prog.backward_timed(dout, noisy) for _ in range(3)])
 
     def agg(table, name):
         sel = [(meta, m) for n, meta, m in table if n == name]
@@ -446,7 +457,7 @@ def main():
     eps = torch.empty(shape, device=dev)
     tf = torch.full((B,), 500.0, device=dev)
     prog.run_timed(sess.x, tf, eps)  # warm
-    table = prog.run_timed(sess.x, tf, eps)
+    table = median_table([prog.run_timed(sess.x, tf, eps) for _ in range(5)])
     conv_ms = sum(m for n, meta, m in table if n == "conv")
     conv_fl = sum(meta["flops"] for n, meta, m in table if n == "conv")
     n_conv = sum(1 for n, meta, m in table if n == "conv")
