@@ -103,13 +103,12 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
           for (int u = 0; u < 8; ++u) f[j * 8 + u] += r[u];
         }
       }
-      __half* op = out + off[m] + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing
     }
+    // the statistics arithmetic comes BEFORE the stores: placed after them, its first instructions overwrote registers the
+    // STG.128s had not read yet and sat on that hazard (every lane stores to its own 128-byte line, the store path is slow)
     if (sstat_warp) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -121,6 +120,11 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
         warp_pairsum16x2(a1, a2, lane);
         if (!(lane & 1)) reinterpret_cast<float2*>(sstat_warp)[c * 16 + (lane >> 1)] = make_float2(a1[0], a2[0]);
       }
+    }
+    if (valid[m]) {
+      __half* op = out + off[m] + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));
     }
   }
 }
