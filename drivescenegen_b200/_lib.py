@@ -94,9 +94,11 @@ SIGNATURES = {
     "dsg_device_ok": (C.c_int, []),
     "dsg_ddpm_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
     "dsg_ddim_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
-    "dsg_add_noise": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _p]),
+    "dsg_add_noise": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _i32, _i64, _p]),
+    "dsg_step_advance": (C.c_int, [_p, _p, _p, _i32, _p, _p]),
     "dsg_latent_to_image": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "dsg_image_to_sample": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "dsg_resize_to_sample": (C.c_int, [_p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "dsg_gray_mask": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, C.c_double, _p]),
     "dsg_agent_threshold": (C.c_int, [_p, _i64, _p, _i32, _i64, _i32, _p]),
     "dsg_time_embed": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _i32, _p, _p, _i32, _p, _p, _i32, _p]),

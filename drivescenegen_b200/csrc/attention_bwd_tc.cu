@@ -252,19 +252,12 @@ int launch_attention_bwd_tc(const __half* qkv, const __half* o, const __half* do
   if (head_dim != 8 || tokens % 128 != 0 || tokens > 2048 || tokens < 128) return 1;
   size_t sm = (size_t)tokens * 64 + 2048 + (size_t)tokens * 8 + 64 + 128;
   if (sm < 120 * 1024) sm = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
-  static size_t attr = 0;
-  if (sm > attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) { set_error("attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr = sm;
-  }
-  int sms = 148;
+  static SmemAttrCache attr;
   {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+    cudaError_t e = ensure_dyn_smem(attr, attention_bwd_tc_kernel, sm);
+    if (e != cudaSuccess) { set_error("attention_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
   }
+  const int sms = num_sms();
   const int pairs = n * heads;
   const int grid = pairs < sms ? pairs : sms;
   const float scale = 1.0f / sqrtf(8.0f);

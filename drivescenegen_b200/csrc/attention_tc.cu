@@ -253,16 +253,7 @@ attention_tc_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, in
   }
 }
 
-static int atc_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int atc_sms() { return num_sms(); }
 
 // returns DSG_OK, an error, or 1 when the shape is outside the kernel (head_dim != 8, tokens % 128, tokens > 4096)
 int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int heads, int head_dim, float* dbg,
@@ -270,11 +261,10 @@ int launch_attention_tc(const __half* qkv, __half* out, int n, int tokens, int h
   if (head_dim != 8 || tokens % 128 != 0 || tokens > 4096 || tokens < 128) return 1;
   size_t sm = (size_t)tokens * 32 + ATC_WGS * 2048 + 256 + 2048 + 64 + 128;
   if (sm < 120 * 1024) sm = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
-  static size_t attr = 0;
-  if (sm > attr) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  static SmemAttrCache attr;
+  {
+    cudaError_t e = ensure_dyn_smem(attr, attention_tc_kernel, sm);
     if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr = sm;
   }
   const int pairs = n * heads;
   const int grid = pairs < atc_sms() ? pairs : atc_sms();

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/dsg_b200.h"
 
 namespace dsg {
@@ -35,6 +37,36 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Per-device caches: cudaFuncSetAttribute and the SM count belong to ONE device, and a process may drive several GPUs
+// (pipeline.to('cuda:1'), threaded replicas).  Zero-initialised statics of atomics: safe across threads (a lost race
+// only repeats an idempotent driver call).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct SmemAttrCache { std::atomic<size_t> bytes[kMaxDevices]; };
+template <typename K>
+inline cudaError_t ensure_dyn_smem(SmemAttrCache& c, K kernel, size_t bytes) {
+  const int d = current_device();
+  if (bytes <= c.bytes[d].load(std::memory_order_relaxed)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) c.bytes[d].store(bytes, std::memory_order_relaxed);
+  return e;
+}
+inline int num_sms() {
+  static std::atomic<int> sms[kMaxDevices];
+  const int d = current_device();
+  int v = sms[d].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    if (v <= 0) v = 148;
+    sms[d].store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 #define DSG_CHECK_ARG(cond, ...)       \

@@ -602,11 +602,10 @@ int dsg_conv_out_fused(const void* x_h16, const float* gn_coef, const float* w, 
   DSG_CHECK_ARG((uintptr_t)x_h16 % 16 == 0 && (uintptr_t)gn_coef % 8 == 0, "dsg_conv_out_fused: unaligned pointer");
   if (n == 0) return DSG_OK;
   const size_t sm = (size_t)2 * CO_WIN_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_out_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  static SmemAttrCache attr;
+  {
+    cudaError_t e = ensure_dyn_smem(attr, conv_out_mma_kernel, (size_t)sm);
     if (e != cudaSuccess) { set_error("dsg_conv_out_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr_set = true;
   }
   const int64_t items = (int64_t)n * ((h + CO_ROWS - 1) / CO_ROWS) * ((wd + CO_TW - 1) / CO_TW);
   const int64_t blocks = items < 148 * 2 ? items : 148 * 2;

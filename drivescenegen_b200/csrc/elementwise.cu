@@ -71,10 +71,13 @@ __global__ void __launch_bounds__(256) add_noise_kernel(const float* __restrict_
                                                         const int64_t* __restrict__ t,
                                                         const float* __restrict__ sqrt_ac,
                                                         const float* __restrict__ sqrt_1mac, float* __restrict__ out,
-                                                        int64_t per_sample) {
+                                                        int64_t per_sample, int32_t table_len) {
   const int n = blockIdx.y;
   const int64_t tt = t[n];
-  const float a = sqrt_ac[tt], b = sqrt_1mac[tt];
+  // a timestep outside the table raises IndexError upstream; here the sample's output is poisoned with NaN instead of
+  // reading out of bounds (the host wrapper range-checks timesteps it can see without a device sync)
+  const bool ok = tt >= 0 && tt < table_len;
+  const float a = ok ? sqrt_ac[tt] : __int_as_float(0x7fc00000), b = ok ? sqrt_1mac[tt] : a;
   const float* xs = x0 + (int64_t)n * per_sample;
   const float* ns = nz + (int64_t)n * per_sample;
   float* os = out + (int64_t)n * per_sample;
@@ -94,6 +97,21 @@ __global__ void __launch_bounds__(256) add_noise_kernel(const float* __restrict_
   } else {
     for (int64_t i = start; i < per_sample; i += stride)
       os[i] = __fadd_rn(__fmul_rn(a, xs[i]), __fmul_rn(b, ns[i]));
+  }
+}
+
+// One block: the next timestep of the sampling schedule -> the U-Net's per-sample timestep values and the scheduler's
+// coefficient-table row, then advance the device-side step counter.  First node of the captured denoise-step graph, so a
+// replay needs no host-side argument updates at all.
+__global__ void step_advance_kernel(const int32_t* __restrict__ schedule, int32_t* __restrict__ state,
+                                    float* __restrict__ t_f, int32_t batch, int32_t* __restrict__ row) {
+  const int k = state[0], n_steps = state[1];
+  const int t = schedule[k < n_steps ? k : n_steps - 1];
+  for (int i = threadIdx.x; i < batch; i += blockDim.x) t_f[i] = (float)t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *row = t;
+    state[0] = k + 1;
   }
 }
 
@@ -156,15 +174,25 @@ int dsg_ddim_step(const float* eps, const float* sample, const float* noise, flo
 }
 
 int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
-                  const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, void* stream) {
-  DSG_CHECK_ARG(batch >= 0 && batch <= 65535 && per_sample >= 0, "dsg_add_noise: bad batch/per_sample");
+                  const float* sqrt_1mac, int32_t table_len, float* out, int32_t batch, int64_t per_sample,
+                  void* stream) {
+  DSG_CHECK_ARG(batch >= 0 && batch <= 65535 && per_sample >= 0 && table_len > 0,
+                "dsg_add_noise: bad batch/per_sample/table_len");
   if (batch == 0 || per_sample == 0) return DSG_OK;
   DSG_CHECK_ARG(x0 && noise && t && sqrt_ac && sqrt_1mac && out, "dsg_add_noise: null pointer");
   DSG_CHECK_ARG(((uintptr_t)x0 | (uintptr_t)noise | (uintptr_t)out) % 16 == 0,
                 "dsg_add_noise: pointers must be 16-byte aligned");
   dim3 grid(grid_for(per_sample / 4 + 1, 256, 148 * 2), batch);
-  add_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample);
+  add_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, noise, t, sqrt_ac, sqrt_1mac, out, per_sample,
+                                                          table_len);
   DSG_CUDA_LAUNCH_CHECK("dsg_add_noise");
+  return DSG_OK;
+}
+
+int dsg_step_advance(const int32_t* schedule, int32_t* state, float* t_f, int32_t batch, int32_t* row, void* stream) {
+  DSG_CHECK_ARG(schedule && state && t_f && row && batch > 0, "dsg_step_advance: bad arguments");
+  step_advance_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(schedule, state, t_f, batch, row);
+  DSG_CUDA_LAUNCH_CHECK("dsg_step_advance");
   return DSG_OK;
 }
 

@@ -459,12 +459,10 @@ static int launch_igemm(const IgPlan& plan_in, cudaStream_t st) {
   }
   int rc = make_map_b(&maps.b, p.w, p.k_total, (int64_t)p.phases * p.cout, BLOCK_N);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+  static SmemAttrCache attr;
+  {
+    cudaError_t e = ensure_dyn_smem(attr, igemm_kernel<BLOCK_N>, (size_t)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr_set = true;
   }
   int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   launch_k(igemm_kernel<BLOCK_N>, dim3((unsigned)grid), dim3(IG_THREADS), Cfg::SMEM_BYTES, st, maps, p);

@@ -223,16 +223,6 @@ inline int make_map_b(CUtensorMap* m, const __half* w, int64_t k_total, int64_t 
   return DSG_OK;
 }
 
-inline int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
 
 inline IgSrc dense_src(const void* ptr, int C, int H, int W) {
   IgSrc s;

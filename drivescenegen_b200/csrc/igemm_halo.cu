@@ -581,12 +581,10 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.stats = (long long*)a->out_stats;
   p.coef = (const float2*)a->gn_coef; p.cin_main = a->cin; p.IH = a->h; p.IW = a->w;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static SmemAttrCache attr;
+  {
+    cudaError_t e = ensure_dyn_smem(attr, igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>, (size_t)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr_set = true;
   }
   const int threads = FUSE ? HL_THREADS_FUSED : HL_THREADS;
   const int64_t slots = num_sms() / CG;  // CTAs, or CTA pairs

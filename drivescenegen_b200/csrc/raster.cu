@@ -72,6 +72,66 @@ __global__ void __launch_bounds__(256) image_to_sample_scalar_kernel(const uint8
       dst[(int64_t)ch * hw + p] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[p * c_img + ch], 255.0f), 0.5f), 0.5f);
 }
 
+// ------------------------------------------------------------------------------------------------ resize -> sample
+// Resize((H, W), antialias=False) of Image_Dataset (dataset.py:20-23) between ToTensor and Normalize: torchvision's
+// tensor resize is ATen's CPU upsample_bilinear2d (align_corners = False), restated bit for bit
+// (oracle/raster.py::resize_bilinear, pinned by tests/golden/resize_golden.npz which torchvision produced):
+//   src = max(fma(scale, i + 0.5, -0.5), 0), scale = float(in) / float(out); i0 = min(int(src), in - 1);
+//   i1 = i0 + (i0 < in - 1); l1 = clamp(src - i0, 0, 1); l0 = 1 - l1; equal sizes: plain copy (weights 1, 0)
+//   mode 0 (ATen's generic N-d kernel: the multi-threaded host path for outputs with H + W > 128, i.e. the reference's
+//           512^2 -> 256^2):  out = fma(top, ly0, bot * ly1), top = fma(a, lx0, b * lx1), bot = fma(c, lx0, d * lx1)
+//   mode 1 (ATen's channels-last kernel: single-threaded hosts with C == 3, and outputs with H + W <= 128):
+//           w00 = ly0 * lx0 ...; out = fma(d, w11, fma(c, w10, fma(a, w00, b * w01)))
+struct ResizeTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ ResizeTap resize_tap(int o, int in_size, int out_size, float scale) {
+  ResizeTap t;
+  if (in_size == out_size) {
+    t.i0 = t.i1 = o; t.l0 = 1.0f; t.l1 = 0.0f;
+    return t;
+  }
+  const float src = fmaxf(__fmaf_rn(scale, __fadd_rn((float)o, 0.5f), -0.5f), 0.0f);
+  t.i0 = min((int)src, in_size - 1);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.l1 = fminf(fmaxf(__fsub_rn(src, (float)t.i0), 0.0f), 1.0f);
+  t.l0 = __fsub_rn(1.0f, t.l1);
+  return t;
+}
+template <typename T> __device__ __forceinline__ float to_unit(T v);
+template <> __device__ __forceinline__ float to_unit<uint8_t>(uint8_t v) { return __fdiv_rn((float)v, 255.0f); }  // ToTensor
+template <> __device__ __forceinline__ float to_unit<float>(float v) { return v; }   // the .pkl branch holds floats
+
+// One thread per output pixel (x fastest): 4 taps x c_img values in (rows y0 / y1 of the NHWC image), c_out coalesced
+// plane stores out.  Grid (x blocks, out_h, n).
+template <typename T>
+__global__ void __launch_bounds__(256) resize_to_sample_kernel(const T* __restrict__ img, float* __restrict__ out,
+                                                               int h, int w, int c_img, int c_out, int out_h, int out_w,
+                                                               float scale_h, float scale_w, int mode) {
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  if (ox >= out_w) return;
+  const ResizeTap ty = resize_tap(oy, h, out_h, scale_h);
+  const ResizeTap tx = resize_tap(ox, w, out_w, scale_w);
+  const T* base = img + (int64_t)n * h * w * c_img;
+  const T* r0 = base + (int64_t)ty.i0 * w * c_img;
+  const T* r1 = base + (int64_t)ty.i1 * w * c_img;
+  float* dst = out + ((int64_t)n * c_out * out_h + oy) * out_w + ox;
+  const float w00 = __fmul_rn(ty.l0, tx.l0), w01 = __fmul_rn(ty.l0, tx.l1);
+  const float w10 = __fmul_rn(ty.l1, tx.l0), w11 = __fmul_rn(ty.l1, tx.l1);
+  for (int ch = 0; ch < c_out; ++ch) {
+    const float a = to_unit<T>(r0[tx.i0 * c_img + ch]), b = to_unit<T>(r0[tx.i1 * c_img + ch]);
+    const float c = to_unit<T>(r1[tx.i0 * c_img + ch]), d = to_unit<T>(r1[tx.i1 * c_img + ch]);
+    float v;
+    if (mode == 0) {
+      const float top = __fmaf_rn(a, tx.l0, __fmul_rn(b, tx.l1));
+      const float bot = __fmaf_rn(c, tx.l0, __fmul_rn(d, tx.l1));
+      v = __fmaf_rn(top, ty.l0, __fmul_rn(bot, ty.l1));
+    } else {
+      v = __fmaf_rn(d, w11, __fmaf_rn(c, w10, __fmaf_rn(a, w00, __fmul_rn(b, w01))));
+    }
+    dst[(int64_t)ch * out_h * out_w] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);   // Normalize([0.5], [0.5])
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ histogram
 // np.histogram(v / 255.0, bins=256, range=(0, 1)) for one byte value: the uniform-bin path computes
 // floor((x - 0) / (1 - 0) * 256) in float64, moves 256 to 255 and then corrects against the edges i / 256 (exact).
@@ -326,6 +386,28 @@ int dsg_image_to_sample(const uint8_t* img, float* out, int32_t n, int32_t h, in
     image_to_sample_scalar_kernel<<<dim3(blocks_for(hw, 256, n), n), 256, 0, st>>>(img, out, c_img, c_out, hw);
   }
   DSG_CUDA_LAUNCH_CHECK("dsg_image_to_sample");
+  return DSG_OK;
+}
+
+int dsg_resize_to_sample(const void* img, int32_t img_is_f32, float* out, int32_t n, int32_t h, int32_t w, int32_t c_img,
+                         int32_t c_out, int32_t out_h, int32_t out_w, int32_t mode, void* stream) {
+  DSG_CHECK_ARG(n >= 0 && n <= 65535 && h > 0 && w > 0 && out_h > 0 && out_h <= 65535 && out_w > 0,
+                "dsg_resize_to_sample: bad shape");
+  DSG_CHECK_ARG(c_img >= 1 && c_out >= 1 && c_out <= c_img, "dsg_resize_to_sample: 1 <= c_out <= c_img");
+  DSG_CHECK_ARG(mode == 0 || mode == 1, "dsg_resize_to_sample: mode is 0 (generic) or 1 (channels-last formula)");
+  if (n == 0) return DSG_OK;
+  DSG_CHECK_ARG(img && out, "dsg_resize_to_sample: null pointer");
+  const float scale_h = (float)h / (float)out_h, scale_w = (float)w / (float)out_w;
+  dim3 grid((unsigned)ceil_div(out_w, 256), (unsigned)out_h, (unsigned)n);
+  const int threads = out_w >= 256 ? 256 : ((out_w + 31) / 32) * 32;
+  if (img_is_f32)
+    resize_to_sample_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>((const float*)img, out, h, w, c_img, c_out,
+                                                                                out_h, out_w, scale_h, scale_w, mode);
+  else
+    resize_to_sample_kernel<uint8_t><<<grid, threads, 0, (cudaStream_t)stream>>>((const uint8_t*)img, out, h, w, c_img,
+                                                                                  c_out, out_h, out_w, scale_h, scale_w,
+                                                                                  mode);
+  DSG_CUDA_LAUNCH_CHECK("dsg_resize_to_sample");
   return DSG_OK;
 }
 

@@ -554,11 +554,10 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
   p.ws = (float*)a->workspace;
 
   const int smem_bytes = WG_RING_BYTES + 256 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static SmemAttrCache attr;
+  {
+    cudaError_t e = ensure_dyn_smem(attr, wgrad_kernel, (size_t)smem_bytes);
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
-    attr_set = true;
   }
   launch_k(wgrad_kernel, dim3((unsigned)splits, (unsigned)items), dim3(WG_THREADS), smem_bytes, st, maps, p);
   DSG_CUDA_LAUNCH_CHECK("dsg_conv_wgrad/tcgen05");

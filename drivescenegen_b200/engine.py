@@ -850,7 +850,8 @@ class _Program:
         self.in_ptr = C.c_void_p(sample.data_ptr())
         self.t_ptr = C.c_void_p(t_float.data_ptr())
         self.out_ptr = C.c_void_p(out.data_ptr())
-        st = torch.cuda.current_stream(sample.device).cuda_stream
-        for op in self.ops:
-            op(st)
+        with torch.cuda.device(sample.device):   # launches go to the tensors' device, whatever the caller's current one
+            st = torch.cuda.current_stream(sample.device).cuda_stream
+            for op in self.ops:
+                op(st)
         return out

@@ -475,9 +475,10 @@ class TrainProgram(_Program):
         assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.is_cuda
         self.dout_ptr = C.c_void_p(dout.data_ptr())
         self.in_ptr = C.c_void_p(sample.data_ptr())
-        st = torch.cuda.current_stream(dout.device).cuda_stream
-        for op in self.bwd_ops:
-            op(st)
+        with torch.cuda.device(dout.device):
+            st = torch.cuda.current_stream(dout.device).cuda_stream
+            for op in self.bwd_ops:
+                op(st)
 
     def backward_timed(self, dout: torch.Tensor, sample: torch.Tensor):
         dev = dout.device

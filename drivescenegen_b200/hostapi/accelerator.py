@@ -31,13 +31,16 @@ class AcceleratedOptimizer:
 
     @property
     def state(self):
+        self.accelerator._export_fused_state(self.optimizer)
         return self.optimizer.state
 
     def state_dict(self):
+        self.accelerator._export_fused_state(self.optimizer)
         return self.optimizer.state_dict()
 
     def load_state_dict(self, sd):
         self.optimizer.load_state_dict(sd)
+        self.accelerator._import_fused_state(self.optimizer)
 
     def zero_grad(self, set_to_none: Optional[bool] = None):
         if self.accelerator.sync_gradients:
@@ -57,6 +60,9 @@ class AcceleratedOptimizer:
             acc.scaler.step(self.optimizer, closure) if closure is not None else acc.scaler.step(self.optimizer)
             acc.scaler.update()
             self.step_was_skipped = acc.scaler.get_scale() < before
+            # the scaler moved without the fused path seeing it: re-read its scale / growth counter next time
+            acc._scale_host = None
+            acc._growth_tracker = int(acc.scaler._get_growth_tracker())
         else:
             self.optimizer.step(closure) if closure is not None else self.optimizer.step()
             self.step_was_skipped = False
@@ -91,15 +97,89 @@ class AcceleratedScheduler:
         return getattr(self.scheduler, name)
 
 
-class ShardedDataLoader:
-    """Rank r of N sees batches r, r+N, r+2N, ... (per-rank batch size unchanged), moved to the device."""
+class BatchSamplerShard:
+    """Rank r of N takes batches r, r+N, r+2N, ... of the wrapped batch sampler — only the INDICES are enumerated on
+    every rank; each rank then loads (decodes) its own samples only.  accelerate 0.22.0 semantics for
+    ``split_batches=False, even_batches=True``: every rank runs the same number of steps with the
+    same batch size; a short final batch and the missing batches of the last round are filled with samples from the
+    beginning of the epoch's index stream."""
 
-    def __init__(self, loader, device, rank: int, world: int):
-        self.loader, self.device, self.rank, self.world = loader, device, rank, world
+    def __init__(self, batch_sampler, rank: int, world: int):
+        self.batch_sampler, self.rank, self.world = batch_sampler, rank, world
+        self.batch_size = getattr(batch_sampler, "batch_size", None)
+        self.drop_last = bool(getattr(batch_sampler, "drop_last", False))
 
     def __len__(self):
-        n = len(self.loader)
-        return (n + self.world - 1) // self.world if self.world > 1 else n
+        n = len(self.batch_sampler)
+        return n // self.world if self.drop_last else (n + self.world - 1) // self.world
+
+    def __iter__(self):
+        world, rank, bs = self.world, self.rank, self.batch_size
+        head: List[int] = []        # indices of the epoch's first `world` batches: what the tail is padded from
+        n_head = 0
+        rnd: List[List[int]] = []   # the batches of the round being collected (one per rank)
+        for batch in self.batch_sampler:
+            batch = list(batch)
+            if n_head < world:
+                head.extend(batch)
+                n_head += 1
+            rnd.append(batch)
+            if len(rnd) == world and (bs is None or len(batch) == bs):
+                yield rnd[rank]
+                rnd = []
+        if not rnd or self.drop_last or not head:
+            return
+        if bs is None:
+            bs = len(rnd[0])
+        pool = head
+        while len(pool) < world * bs:
+            pool = pool + pool
+        pos = 0
+        if len(rnd[-1]) < bs:
+            need = bs - len(rnd[-1])
+            rnd[-1] = rnd[-1] + pool[pos:pos + need]
+            pos += need
+        while len(rnd) < world:
+            rnd.append(pool[pos:pos + bs])
+            pos += bs
+        yield rnd[rank]
+
+
+class ShardedDataLoader:
+    """The prepared DataLoader: batches moved to the device; with N ranks, rank r sees batches r, r+N, r+2N, ... (per-rank
+    batch size unchanged) through a DataLoader rebuilt over ``BatchSamplerShard``, and the shuffle generator is
+    synchronised from rank 0 at the start of every epoch (upstream ``synchronize_rng_states(["generator"])``), so the
+    ranks' shards stay disjoint whatever each rank did to its global RNG in between (the reference's ``evaluate`` calls
+    ``torch.manual_seed`` on rank 0 only, training_pipeline.py:29)."""
+
+    def __init__(self, loader, device, rank: int, world: int):
+        self.device, self.rank, self.world = device, rank, world
+        self.base = loader
+        self.sync_generator = None
+        bsamp = getattr(loader, "batch_sampler", None)
+        if world > 1 and bsamp is not None and not isinstance(loader.dataset, torch.utils.data.IterableDataset):
+            sampler = getattr(bsamp, "sampler", None)
+            if isinstance(sampler, torch.utils.data.RandomSampler):
+                if sampler.generator is None:
+                    sampler.generator = torch.Generator()
+                self.sync_generator = sampler.generator
+            kw = dict(num_workers=loader.num_workers, collate_fn=loader.collate_fn, pin_memory=loader.pin_memory,
+                      timeout=loader.timeout, worker_init_fn=loader.worker_init_fn,
+                      multiprocessing_context=loader.multiprocessing_context, generator=loader.generator,
+                      persistent_workers=loader.persistent_workers)
+            if loader.num_workers > 0:
+                kw["prefetch_factor"] = loader.prefetch_factor
+            self.loader = torch.utils.data.DataLoader(loader.dataset, batch_sampler=BatchSamplerShard(bsamp, rank, world),
+                                                      **kw)
+            self.sharded_by_sampler = True
+        else:
+            self.loader = loader
+            self.sharded_by_sampler = False
+
+    def __len__(self):
+        if self.sharded_by_sampler or self.world == 1:
+            return len(self.loader)
+        return (len(self.loader) + self.world - 1) // self.world
 
     @property
     def dataset(self):
@@ -107,16 +187,18 @@ class ShardedDataLoader:
 
     @property
     def batch_size(self):
-        return self.loader.batch_size
+        return self.base.batch_size
 
     def _move(self, b):
         if torch.is_tensor(b):
             if self.device.type == "cuda":
                 from . import raster
-                if raster.is_raster_batch(b):
-                    # RasterDataset batches cross PCIe as bytes and are normalised on the device (dsg_image_to_sample)
+                if raster.is_raster_batch(b, self.base.dataset):
+                    # RasterDataset batches cross PCIe as bytes; resample + normalise run on the device
                     src = b if b.is_cuda or b.is_pinned() else b.pin_memory()
-                    return raster.image_to_sample(src.to(self.device, non_blocking=True), channels=min(3, b.shape[3]))
+                    size = getattr(self.base.dataset, "size", None)
+                    return raster.image_to_sample(src.to(self.device, non_blocking=True), channels=min(3, b.shape[3]),
+                                                  size=size)
             return b.to(self.device, non_blocking=True)
         if isinstance(b, (list, tuple)):
             return type(b)(self._move(x) for x in b)
@@ -124,12 +206,23 @@ class ShardedDataLoader:
             return {k: self._move(v) for k, v in b.items()}
         return b
 
+    def _sync_rng(self):
+        if self.sync_generator is None or not dist.is_initialized():
+            return
+        state = self.sync_generator.get_state()
+        dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = state.to(dev)
+        dist.broadcast(t, src=0)
+        self.sync_generator.set_state(t.cpu())
+
     def __iter__(self):
-        if self.world == 1:
+        if self.world == 1 or self.sharded_by_sampler:
+            self._sync_rng()
             for b in self.loader:
                 yield self._move(b)
             return
-        # every rank must run the same number of steps: the tail is padded by wrapping around (even_batches=True)
+        # no batch sampler to shard (iterable dataset): every rank walks the stream and keeps its own batches; the tail
+        # is padded by wrapping around so that every rank runs the same number of steps
         batches, first = [], []
         for i, b in enumerate(self.loader):
             if len(first) < self.world:
@@ -367,6 +460,49 @@ class Accelerator:
                 self.scaler.update(new_scale=scale)
                 self._scale_host = scale
         return True
+
+    # The fused kernel keeps AdamW's moments in two flat buffers.  torch's optimizer state is made to ALIAS them
+    # (per-parameter views), so optimizer.state / state_dict() / load_state_dict() — checkpoint and resume — see the
+    # real moments and the real bias-correction step.
+    def _export_fused_state(self, opt):
+        st = self._fused_state.get(id(opt))
+        if st is None:
+            return
+        off = 0
+        for p in opt.param_groups[0]["params"]:
+            n = p.numel()
+            s = opt.state[p]
+            m = s.get("exp_avg")
+            if m is None or m.data_ptr() != st["m"].data_ptr() + 4 * off:
+                s["exp_avg"] = st["m"][off:off + n].view_as(p)
+                s["exp_avg_sq"] = st["v"][off:off + n].view_as(p)
+            s["step"] = torch.tensor(float(st["step"]))
+            off += n
+
+    def _import_fused_state(self, opt):
+        if len(opt.param_groups) != 1:
+            return
+        params = opt.param_groups[0]["params"]
+        if not params or not all("exp_avg" in opt.state.get(p, {}) for p in params):
+            return
+        if len(self._models) != 1 or getattr(self._models[0], "_flat_params", None) is None:
+            return
+        flat_p = self._models[0]._flat_params
+        if sum(p.numel() for p in params) != flat_p.numel():
+            return
+        st = self._fused_state.get(id(opt))
+        if st is None:
+            st = {"m": torch.zeros_like(flat_p), "v": torch.zeros_like(flat_p), "step": 0}
+            self._fused_state[id(opt)] = st
+        off = 0
+        for p in params:
+            n = p.numel()
+            s = opt.state[p]
+            st["m"][off:off + n].copy_(s["exp_avg"].reshape(-1))
+            st["v"][off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+            off += n
+        st["step"] = int(float(opt.state[params[0]]["step"]))
+        self._export_fused_state(opt)
 
     def unwrap_model(self, model, keep_fp32_wrapper: bool = True):
         return model

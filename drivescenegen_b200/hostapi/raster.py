@@ -49,18 +49,55 @@ def _as_u8_batch(images, device=None) -> torch.Tensor:
     return images.contiguous()
 
 
-def image_to_sample(images, channels: int = 3, out: torch.Tensor = None, device=None) -> torch.Tensor:
-    """uint8 rasters [n,h,w,c] (or one [h,w,c]) -> normalised fp32 samples [n,channels,h,w] in [-1, 1]."""
-    img = _as_u8_batch(images, device)
+def aten_resize_mode(out_h: int, out_w: int, channels: int, host_threads: int = None) -> int:
+    """Which of ATen's two CPU bilinear kernels the reference's ``Resize(antialias=False)`` would have run on the host
+    (they differ in the last bit): 1 = the channels-last kernel, taken by single-threaded hosts for 3-channel images and
+    (observed with torch 2.11, recorded in tests/golden/resize_golden.npz) by outputs with ``out_h + out_w <= 128``;
+    0 = the generic N-d kernel, i.e. the reference's 512^2 -> 256^2 on any multi-core host."""
+    if host_threads is None:
+        host_threads = torch.get_num_threads()
+    if out_h + out_w <= 128 or (host_threads == 1 and channels == 3):
+        return 1
+    return 0
+
+
+def image_to_sample(images, channels: int = 3, out: torch.Tensor = None, device=None, size=None,
+                    mode: int = None) -> torch.Tensor:
+    """rasters [n,h,w,c] (or one [h,w,c]) -> normalised fp32 samples [n,channels,H,W] in [-1, 1].
+
+    uint8 rasters go through ToTensor (x / 255); float32 rasters (the ``.pkl`` branch of ``Image_Dataset``) are taken as
+    they are.  ``size=(H, W)`` different from the stored size adds the transform's ``Resize(size, antialias=False)``
+    between ToTensor and Normalize, bit-identical to torchvision on the host; ``mode`` picks ATen's kernel variant
+    (default: :func:`aten_resize_mode`)."""
+    if isinstance(images, torch.Tensor) and images.dtype == torch.float32:
+        img = images[None] if images.dim() == 3 else images
+        if img.dim() != 4:
+            raise ValueError(f"expected [h,w,c] or [n,h,w,c] rasters, got shape {tuple(images.shape)}")
+        if not img.is_cuda:
+            img = img.to(_device(device), non_blocking=True)
+        img = img.contiguous()
+    else:
+        img = _as_u8_batch(images, device)
     n, h, w, c = img.shape
     if not 1 <= channels <= c:
         raise ValueError(f"channels={channels} but the images have {c}")
+    oh, ow = (h, w) if size is None else (int(size[0]), int(size[1]))
     if out is None:
-        out = torch.empty((n, channels, h, w), dtype=torch.float32, device=img.device)
-    elif out.shape != (n, channels, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != img.device:
-        raise ValueError("out must be a contiguous fp32 tensor [n,channels,h,w] on the images' device")
-    check(_lib.load().dsg_image_to_sample(img.data_ptr(), out.data_ptr(), n, h, w, c, channels, _stream(img.device)),
-          "dsg_image_to_sample")
+        out = torch.empty((n, channels, oh, ow), dtype=torch.float32, device=img.device)
+    elif out.shape != (n, channels, oh, ow) or out.dtype != torch.float32 or not out.is_contiguous() \
+            or out.device != img.device:
+        raise ValueError("out must be a contiguous fp32 tensor [n,channels,H,W] on the images' device")
+    lib = _lib.load()
+    with torch.cuda.device(img.device):
+        if (oh, ow) == (h, w) and img.dtype == torch.uint8 and c <= 4:
+            check(lib.dsg_image_to_sample(img.data_ptr(), out.data_ptr(), n, h, w, c, channels, _stream(img.device)),
+                  "dsg_image_to_sample")
+        else:
+            if mode is None:
+                mode = aten_resize_mode(oh, ow, channels)
+            check(lib.dsg_resize_to_sample(img.data_ptr(), 1 if img.dtype == torch.float32 else 0, out.data_ptr(), n, h,
+                                           w, c, channels, oh, ow, int(mode), _stream(img.device)),
+                  "dsg_resize_to_sample")
     return out
 
 
@@ -76,9 +113,10 @@ def gray_masks(images, thresh: float = 0.1, want_gray3: bool = False, device=Non
     peaks = torch.empty((n, 3), dtype=torch.int32, device=dev)
     mask = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     gray3 = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev) if want_gray3 else None
-    check(_lib.load().dsg_gray_mask(img.data_ptr(), hist.data_ptr(), peaks.data_ptr(), mask.data_ptr(),
-                                    gray3.data_ptr() if want_gray3 else None, n, h, w, c, float(thresh), _stream(dev)),
-          "dsg_gray_mask")
+    with torch.cuda.device(dev):
+        check(_lib.load().dsg_gray_mask(img.data_ptr(), hist.data_ptr(), peaks.data_ptr(), mask.data_ptr(),
+                                        gray3.data_ptr() if want_gray3 else None, n, h, w, c, float(thresh),
+                                        _stream(dev)), "dsg_gray_mask")
     return (gray3 if want_gray3 else mask), peaks, hist
 
 
@@ -108,8 +146,9 @@ def agent_threshold(raw_img: torch.Tensor, thresh: int = 100, channel: int = 2) 
     n, c, h, w = x.shape
     out = torch.empty((n, h, w), dtype=torch.uint8, device=x.device)
     plane = x.data_ptr() + channel * h * w * 4
-    check(_lib.load().dsg_agent_threshold(plane, c * h * w, out.data_ptr(), n, h * w, int(thresh), _stream(x.device)),
-          "dsg_agent_threshold")
+    with torch.cuda.device(x.device):
+        check(_lib.load().dsg_agent_threshold(plane, c * h * w, out.data_ptr(), n, h * w, int(thresh),
+                                              _stream(x.device)), "dsg_agent_threshold")
     return out
 
 
@@ -117,11 +156,13 @@ class RasterDataset(torch.utils.data.Dataset):
     """``Image_Dataset`` (DriveSceneGen/utils/datasets/dataset.py:15-50) with the arithmetic left for the device.
 
     Same constructor argument (``config.dataset_name`` glob, ``patterns_size_height/width``), same ``data_list`` /
-    ``remove_sample``; ``__getitem__`` only decodes the PNG and returns the uint8 ``[h, w, c]`` raster.  A DataLoader over
-    it collates uint8 ``[b, h, w, c]`` batches; ``Accelerator.prepare`` (ShardedDataLoader) ships those bytes to the GPU
-    and runs ``dsg_image_to_sample`` there, so the training loop still receives the reference's normalised fp32
-    ``[b, 3, h, w]`` batch, bit-identical.  Rasters must be stored at the model's size (the reference's Resize is then the
-    identity); anything else raises instead of silently resampling.
+    ``remove_sample``; ``__getitem__`` only decodes the file and returns the raw ``[h, w, c]`` raster at its STORED size:
+    uint8 for images, float32 for the ``.pkl`` branch (``torch.load(f)['fig_tensor']``, dataset.py:38-42; a non-dict
+    pickle falls through to the next item like the reference).  A DataLoader over it collates ``[b, h, w, c]`` batches;
+    ``Accelerator.prepare`` (ShardedDataLoader) ships those bytes to the GPU and runs ToTensor + ``Resize((H, W),
+    antialias=False)`` + ``Normalize`` there (``dsg_image_to_sample`` / ``dsg_resize_to_sample``), so the training loop
+    still receives the reference's fp32 ``[b, 3, H, W]`` batch, bit-identical.  All files of one dataset must share one
+    stored size (the reference's rasteriser writes 512^2) — the batch is collated before it is resampled.
     """
 
     def __init__(self, config):
@@ -137,17 +178,32 @@ class RasterDataset(torch.utils.data.Dataset):
         del self.data_list[index]
 
     def __getitem__(self, index):
+        import os
+        file = self.data_list[index]
+        if os.path.splitext(file)[1].lower() == ".pkl":
+            with open(file, "rb") as f:
+                data = torch.load(f, weights_only=False)
+            if not isinstance(data, dict):
+                return self.__getitem__(index + 1)
+            fig = data["fig_tensor"][:, :, :]
+            if fig.dtype != torch.float32:
+                raise ValueError(f"{file}: fig_tensor must be float32, got {fig.dtype}")
+            return fig.contiguous()
         from PIL import Image
-        with open(self.data_list[index], "rb") as f:
+        with open(file, "rb") as f:
             arr = np.array(Image.open(f))
         if arr.ndim == 2:
             arr = arr[:, :, None]
-        if arr.dtype != np.uint8 or arr.shape[:2] != self.size:
-            raise ValueError(f"{self.data_list[index]}: expected an 8-bit raster of size {self.size}, got "
-                             f"{arr.dtype} {arr.shape} (resize offline; the device path does not resample)")
+        if arr.dtype != np.uint8:
+            raise ValueError(f"{file}: expected an 8-bit raster, got {arr.dtype}")
         return torch.from_numpy(arr)
 
 
-def is_raster_batch(t) -> bool:
-    """A collated batch of RasterDataset items: uint8 [b, h, w, c] with c <= 4."""
-    return torch.is_tensor(t) and t.dtype == torch.uint8 and t.dim() == 4 and 1 <= t.shape[3] <= 4
+def is_raster_batch(t, dataset=None) -> bool:
+    """A collated batch of RasterDataset items: [b, h, w, c] uint8 with c <= 4 (or any dtype RasterDataset returns when
+    the loader's dataset is known to be one)."""
+    if not torch.is_tensor(t) or t.dim() != 4:
+        return False
+    if isinstance(dataset, RasterDataset):
+        return t.dtype in (torch.uint8, torch.float32)
+    return t.dtype == torch.uint8 and 1 <= t.shape[3] <= 4

@@ -20,7 +20,6 @@ import torch
 from .. import _lib
 from .._lib import DsgError, check
 from .configuration import ConfigMixin
-from .. import testing as _testing
 
 
 def randn_tensor(shape, generator=None, device=None, dtype=None):
@@ -97,9 +96,6 @@ class _SchedulerBase(ConfigMixin):
     # -------------------------------------------------------------- add_noise (shared by DDPM and DDIM)
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor):
         if not original_samples.is_cuda:
-            hook = _testing.cpu_backend("add_noise")
-            if hook is not None:
-                return hook(self, original_samples, noise, timesteps)
             raise DsgError("add_noise: CUDA tensors required (no CPU arithmetic path in the product)")
         dev = original_samples.device
         key = str(dev)
@@ -109,6 +105,9 @@ class _SchedulerBase(ConfigMixin):
         sa, sb = self._noise_tables[key]
         x0 = _as_f32_cuda(original_samples, "add_noise")
         nz = _as_f32_cuda(noise.to(dev), "add_noise")
+        if not timesteps.is_cuda:   # free to check on the host (upstream: IndexError); device tensors are guarded in-kernel
+            if timesteps.numel() and (int(timesteps.min()) < 0 or int(timesteps.max()) >= sa.numel()):
+                raise IndexError(f"add_noise: timestep outside [0, {sa.numel()})")
         t = timesteps.to(dev, torch.int64).contiguous().flatten()
         batch = x0.shape[0] if t.numel() > 1 else 1
         if t.numel() not in (1, x0.shape[0]):
@@ -116,8 +115,9 @@ class _SchedulerBase(ConfigMixin):
         per = x0.numel() // batch
         out = torch.empty_like(x0)
         lib = _lib.load()
-        check(lib.dsg_add_noise(x0.data_ptr(), nz.data_ptr(), t.data_ptr(), sa.data_ptr(), sb.data_ptr(),
-                                out.data_ptr(), batch, per, _stream(dev)), "dsg_add_noise")
+        with torch.cuda.device(dev):
+            check(lib.dsg_add_noise(x0.data_ptr(), nz.data_ptr(), t.data_ptr(), sa.data_ptr(), sb.data_ptr(),
+                                    sa.numel(), out.data_ptr(), batch, per, _stream(dev)), "dsg_add_noise")
         return out
 
 
@@ -191,10 +191,6 @@ class DDPMScheduler(_SchedulerBase):
              return_dict: bool = True, variance_noise: Optional[torch.Tensor] = None):
         t = int(timestep)
         if not sample.is_cuda:
-            hook = _testing.cpu_backend("ddpm_step")
-            if hook is not None:
-                prev = hook(self, model_output, t, sample, generator)
-                return SchedulerOutput(prev_sample=prev) if return_dict else (prev,)
             raise DsgError("DDPMScheduler.step: CUDA tensors required (no CPU arithmetic path in the product)")
         dev = sample.device
         eps = _as_f32_cuda(model_output, "step")
@@ -206,8 +202,10 @@ class DDPMScheduler(_SchedulerBase):
             z = _as_f32_cuda(z, "step")
         prev = torch.empty_like(x)
         lib = _lib.load()
-        check(lib.dsg_ddpm_step(eps.data_ptr(), x.data_ptr(), None if z is None else z.data_ptr(), prev.data_ptr(),
-                                x.numel(), self.coef_table(dev).data_ptr(), None, t, _stream(dev)), "dsg_ddpm_step")
+        with torch.cuda.device(dev):
+            check(lib.dsg_ddpm_step(eps.data_ptr(), x.data_ptr(), None if z is None else z.data_ptr(),
+                                    prev.data_ptr(), x.numel(), self.coef_table(dev).data_ptr(), None, t,
+                                    _stream(dev)), "dsg_ddpm_step")
         if not return_dict:
             return (prev,)
         return SchedulerOutput(prev_sample=prev)
@@ -269,10 +267,6 @@ class DDIMScheduler(_SchedulerBase):
             raise NotImplementedError("use_clipped_model_output=True is not supported")
         t = int(timestep)
         if not sample.is_cuda:
-            hook = _testing.cpu_backend("ddim_step")
-            if hook is not None:
-                prev = hook(self, model_output, t, sample, eta, generator)
-                return SchedulerOutput(prev_sample=prev) if return_dict else (prev,)
             raise DsgError("DDIMScheduler.step: CUDA tensors required (no CPU arithmetic path in the product)")
         dev = sample.device
         eps = _as_f32_cuda(model_output, "step")
@@ -284,9 +278,10 @@ class DDIMScheduler(_SchedulerBase):
             z = _as_f32_cuda(z, "step")
         prev = torch.empty_like(x)
         lib = _lib.load()
-        check(lib.dsg_ddim_step(eps.data_ptr(), x.data_ptr(), None if z is None else z.data_ptr(), prev.data_ptr(),
-                                x.numel(), self.coef_table(dev, eta).data_ptr(), None, t, _stream(dev)),
-              "dsg_ddim_step")
+        with torch.cuda.device(dev):
+            check(lib.dsg_ddim_step(eps.data_ptr(), x.data_ptr(), None if z is None else z.data_ptr(),
+                                    prev.data_ptr(), x.numel(), self.coef_table(dev, eta).data_ptr(), None, t,
+                                    _stream(dev)), "dsg_ddim_step")
         if not return_dict:
             return (prev,)
         return SchedulerOutput(prev_sample=prev)

@@ -7,7 +7,7 @@ return_dict=False)[0]`` ``DriveSceneGen/pipeline/training_pipeline.py:84``; ``un
 
 This class holds the parameter tree under upstream's names (state-dict compatible) and the
 constructor/validation logic; it contains NO torch arithmetic.  ``forward`` on CUDA tensors runs ``UNetEngine``
-(hand-written CUDA behind the C ABI); on CPU tensors it raises unless the test-suite registered a CPU backend.
+(hand-written CUDA behind the C ABI); on CPU tensors it raises.
 """
 from __future__ import annotations
 
@@ -19,7 +19,6 @@ from typing import Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .. import testing as _testing
 from .._lib import DsgError
 from ..engine import UNetEngine
 from .configuration import ConfigMixin
@@ -217,10 +216,6 @@ class UNet2DModel(nn.Module, ConfigMixin):
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 class_labels: Optional[torch.Tensor] = None, return_dict: bool = True):
         if not sample.is_cuda:
-            hook = _testing.cpu_backend("unet_forward")
-            if hook is not None:
-                out = hook(self, sample, timestep)
-                return UNet2DOutput(sample=out) if return_dict else (out,)
             raise DsgError("UNet2DModel.forward: CUDA tensors required (dsg_b200 has no CPU arithmetic path)")
         if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
             from .training import unet_forward_with_grad  # backward kernels (training path)

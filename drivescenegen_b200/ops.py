@@ -44,7 +44,7 @@ def add_noise(x0, noise, t, sqrt_ac, sqrt_1mac):
     out = torch.empty_like(x0)
     b = x0.shape[0]
     check(lib.dsg_add_noise(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), sqrt_ac.data_ptr(), sqrt_1mac.data_ptr(),
-                            out.data_ptr(), b, x0.numel() // b, _st(x0)), "add_noise")
+                            sqrt_ac.numel(), out.data_ptr(), b, x0.numel() // b, _st(x0)), "add_noise")
     return out
 
 

@@ -51,9 +51,17 @@ int dsg_ddpm_step(const float* eps, const float* sample, const float* noise /* m
                   int64_t numel, const float* coef_table, const int32_t* row_dev, int32_t row, void* stream);
 int dsg_ddim_step(const float* eps, const float* sample, const float* noise /* may be NULL */, float* prev,
                   int64_t numel, const float* coef_table, const int32_t* row_dev, int32_t row, void* stream);
-/* DDPMScheduler.add_noise: out = sqrt_ac[t[n]] * x0 + sqrt_1mac[t[n]] * noise ; t is int64[batch] */
+/* DDPMScheduler.add_noise: out = sqrt_ac[t[n]] * x0 + sqrt_1mac[t[n]] * noise ; t is int64[batch].  The tables hold
+ * table_len entries; a timestep outside [0, table_len) (IndexError upstream) yields an all-NaN sample, never an
+ * out-of-bounds read. */
 int dsg_add_noise(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
-                  const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, void* stream);
+                  const float* sqrt_1mac, int32_t table_len, float* out, int32_t batch, int64_t per_sample,
+                  void* stream);
+/* Sampling-loop bookkeeping of DDPMPipeline.__call__ (`for t in self.scheduler.timesteps`, reached from
+ * DriveSceneGen/scripts/generation.py:14) on the device: state = {k, n_steps}; t = schedule[min(k, n_steps-1)];
+ * t_f[0..batch) = t; *row = t; state[0] = k + 1.  First node of the captured step graph: a replay then takes no
+ * host-side argument updates. */
+int dsg_step_advance(const int32_t* schedule, int32_t* state, float* t_f, int32_t batch, int32_t* row, void* stream);
 /* pipeline post-process: NCHW fp32 latent -> NHWC; u8 = round(clamp(x/2+.5,0,1)*255) (numpy_to_pil) and/or
  * f32 = clamp(x/2+.5,0,1).  Either output may be NULL. */
 int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, int32_t n, int32_t c, int32_t h,
@@ -67,6 +75,15 @@ int dsg_latent_to_image(const float* latent, uint8_t* out_u8, float* out_f32, in
  * when the stored raster already has the model's size; other sizes are the caller's business. */
 int dsg_image_to_sample(const uint8_t* img, float* out, int32_t n, int32_t h, int32_t w, int32_t c_img, int32_t c_out,
                         void* stream);
+/* The same with the transform's Resize((out_h, out_w), antialias=False) (dataset.py:20-23) between ToTensor and
+ * Normalize — the reference rasterises at 512^2 (config/data_rasterization.yaml:6) and trains at 256^2
+ * (scripts/train.py:14-15), so this resample is live on every sample.  Bit-exact restatement of ATen's CPU
+ * upsample_bilinear2d (align_corners = False); mode selects which of ATen's two CPU kernels is reproduced:
+ * 0 = the generic N-d kernel (multi-threaded hosts, out_h + out_w > 128: the reference's case), 1 = the channels-last
+ * kernel (single-threaded hosts with 3 channels, or out_h + out_w <= 128).  img: uint8 [n][h][w][c_img], or
+ * float [n][h][w][c_img] already in [0, 1] when img_is_f32 (the `.pkl` branch, dataset.py:38-42, skips ToTensor). */
+int dsg_resize_to_sample(const void* img, int32_t img_is_f32, float* out, int32_t n, int32_t h, int32_t w, int32_t c_img,
+                         int32_t c_out, int32_t out_h, int32_t out_w, int32_t mode, void* stream);
 /* Vectoriser front end — replaces get_gray_image
  * (DriveSceneGen/vectorization/utils/image_utils.py:13-42) for a batch of rasters that are still on the device.
  *   img   uint8 [n][h][w][c], c = 3 or 4 (channel 0 = dx, 1 = dy, 2 = speed)

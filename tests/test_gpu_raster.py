@@ -202,6 +202,70 @@ def test_raster_dataset_through_accelerator_equals_reference_dataset_arithmetic(
     got = torch.cat(batches).cpu()
     ref = torch.from_numpy(imgs).permute(0, 3, 1, 2).float().div(255).sub(0.5).div(0.5)
     assert got.is_floating_point() and torch.equal(got, ref)
-    bad = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=64, patterns_size_width=64)
-    with pytest.raises(ValueError):
-        RasterDataset(bad)[0]
+
+
+RESIZE_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_golden.npz")
+
+
+def test_golden_resize_to_sample():
+    """dsg_resize_to_sample against what the reference's Image_Dataset (live Resize, .pkl branch) returned."""
+    from drivescenegen_b200.hostapi import raster
+    g = np.load(RESIZE_GOLD)
+    for k in range(int(g["n_cases"])):
+        img, (H, W), ref, mode = g[f"image_{k}"], g[f"size_{k}"], g[f"sample_{k}"], int(g[f"mode_{k}"])
+        src = torch.from_numpy(img) if img.dtype == np.float32 else img
+        got = raster.image_to_sample(src, channels=img.shape[2], size=(int(H), int(W)), mode=mode).cpu().numpy()[0]
+        assert np.array_equal(got, ref), f"case {k} (explicit mode)"
+        # the default rule (host thread count of THIS box; the fixtures were made on a multi-core host)
+        if torch.get_num_threads() > 1:
+            auto = raster.image_to_sample(src, channels=img.shape[2], size=(int(H), int(W))).cpu().numpy()[0]
+            assert np.array_equal(auto, ref), f"case {k} (automatic mode)"
+
+
+@pytest.mark.parametrize("n,h,w,c,co,H,W", [(2, 512, 512, 3, 3, 256, 256), (3, 37, 53, 4, 3, 64, 96),
+                                            (1, 16, 16, 3, 2, 64, 64), (2, 100, 60, 1, 1, 60, 100),
+                                            (16, 512, 512, 3, 3, 256, 256)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_resize_to_sample_vs_oracle(n, h, w, c, co, H, W, mode):
+    from drivescenegen_b200.hostapi import raster
+    from oracle.raster import resize_to_sample
+    rng = np.random.default_rng(h * 7 + w)
+    img = _rand_images(rng, n, h, w, c, dominant=(c >= 3))
+    check = slice(0, 2)   # the numpy oracle on two images is enough at the big batch
+    got = raster.image_to_sample(img, channels=co, size=(H, W), mode=mode).cpu().numpy()
+    assert got.shape == (n, co, H, W)
+    assert np.array_equal(got[check], resize_to_sample(img[check], H, W, c_out=co, mode=mode))
+    if n > 2:   # size-independent property: every image of the batch is processed alike
+        again = raster.image_to_sample(img[-1:], channels=co, size=(H, W), mode=mode).cpu().numpy()
+        assert np.array_equal(got[-1:], again)
+    f = torch.from_numpy(img[check].astype(np.float32) / np.float32(255.0))
+    gotf = raster.image_to_sample(f, channels=co, size=(H, W), mode=mode).cpu().numpy()
+    assert np.array_equal(gotf, resize_to_sample(f.numpy(), H, W, c_out=co, mode=mode))
+
+
+def test_raster_dataset_with_stored_512_rasters_feeds_256_batches(tmp_path):
+    """The reference's real data layout: rasters stored at 512^2 (config/data_rasterization.yaml), model at 256^2
+    (scripts/train.py:14-15).  RasterDataset -> DataLoader -> Accelerator.prepare must hand the loop exactly what
+    Image_Dataset would have: checked against the reference-generated golden sample of case 0."""
+    import types
+    from PIL import Image
+    from drivescenegen_b200.hostapi import Accelerator, RasterDataset
+    g = np.load(RESIZE_GOLD)
+    img, ref = g["image_0"], g["sample_0"]
+    for i in range(3):
+        Image.fromarray(img).save(tmp_path / f"{i}.png")
+    cfg = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=256, patterns_size_width=256)
+    loader = Accelerator().prepare(torch.utils.data.DataLoader(RasterDataset(cfg), batch_size=2, shuffle=False))
+    batches = list(loader)
+    assert [tuple(b.shape) for b in batches] == [(2, 3, 256, 256), (1, 3, 256, 256)]
+    for b in batches:
+        for smp in b.cpu().numpy():
+            assert np.array_equal(smp, ref)
+    # .pkl branch end to end (case 4 of the fixture)
+    k = int(g["n_cases"]) - 1
+    fig, (H, W), refp = g[f"image_{k}"], g[f"size_{k}"], g[f"sample_{k}"]
+    torch.save({"fig_tensor": torch.from_numpy(fig)}, tmp_path / "x.pkl")
+    cfgp = types.SimpleNamespace(dataset_name=str(tmp_path / "*.pkl"), patterns_size_height=int(H),
+                                 patterns_size_width=int(W))
+    (bp,) = list(Accelerator().prepare(torch.utils.data.DataLoader(RasterDataset(cfgp), batch_size=1)))
+    assert np.array_equal(bp.cpu().numpy()[0], refp)

@@ -89,10 +89,19 @@ def test_raster_dataset_host_side_and_no_cpu_path(tmp_path):
     assert len(ds) == 2 and np.array_equal(ds[0].numpy(), imgs[1])
     batch = torch.utils.data.default_collate([ds[0], ds[1]])
     assert raster.is_raster_batch(batch) and not raster.is_raster_batch(batch.float())
+    assert raster.is_raster_batch(batch.float(), ds)                      # float rasters only when the dataset says so
     assert not raster.is_raster_batch(torch.zeros(2, 3, 8, 8))            # a normalised fp32 batch is left alone
-    wrong = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=32, patterns_size_width=32)
-    with pytest.raises(ValueError):
-        RasterDataset(wrong)[0]
+    # stored size != model size is fine (the device resamples); the .pkl branch returns the float fig_tensor, and a
+    # non-dict pickle falls through to the next item (dataset.py:38-42)
+    other = types.SimpleNamespace(dataset_name=str(tmp_path / "*.png"), patterns_size_height=32, patterns_size_width=32)
+    assert tuple(RasterDataset(other)[0].shape) == (24, 40, 3) and RasterDataset(other).size == (32, 32)
+    fig = torch.rand(10, 12, 3)
+    torch.save([1, 2, 3], tmp_path / "a.pkl")
+    torch.save({"fig_tensor": fig}, tmp_path / "b.pkl")
+    pk = RasterDataset(types.SimpleNamespace(dataset_name=str(tmp_path / "*.pkl"), patterns_size_height=8,
+                                             patterns_size_width=8))
+    pk.data_list.sort()
+    assert torch.equal(pk[0], fig) and torch.equal(pk[1], fig)
     if not torch.cuda.is_available():
         for call in (lambda: raster.image_to_sample(imgs), lambda: raster.gray_masks(imgs),
                      lambda: raster.get_gray_image(Image.fromarray(imgs[0])),
@@ -100,4 +109,44 @@ def test_raster_dataset_host_side_and_no_cpu_path(tmp_path):
             with pytest.raises(DsgError):
                 call()
     with pytest.raises(ValueError):
-        raster.image_to_sample(imgs.astype(np.float32))
+        raster.image_to_sample(imgs.astype(np.float64))
+
+
+RESIZE_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_golden.npz")
+
+
+def test_resize_oracle_matches_reference_dataset_with_live_resize():
+    """Image_Dataset with stored size != model size (the reference's 512^2 -> 256^2, non-dyadic 400 -> 256, RGBA, a small
+    output, the .pkl branch): the oracle's restatement of ATen's two CPU bilinear kernels reproduces torchvision bit for
+    bit, and the kernel-selection rule the host API applies picks the variant torchvision actually ran."""
+    from drivescenegen_b200.hostapi.raster import aten_resize_mode
+    from oracle.raster import resize_to_sample
+    g = np.load(RESIZE_GOLD)
+    assert int(g["n_cases"]) >= 5 and int(g["threads"]) > 1
+    seen = set()
+    for k in range(int(g["n_cases"])):
+        img, (H, W), ref, mode = g[f"image_{k}"], g[f"size_{k}"], g[f"sample_{k}"], int(g[f"mode_{k}"])
+        assert mode in (0, 1), "every fixture case distinguishes the two kernels"
+        got = resize_to_sample(img[None], int(H), int(W), mode=mode)[0]
+        assert got.dtype == np.float32 and np.array_equal(got, ref), f"case {k}"
+        assert not np.array_equal(resize_to_sample(img[None], int(H), int(W), mode=1 - mode)[0], ref)
+        assert aten_resize_mode(int(H), int(W), img.shape[2], host_threads=int(g["threads"])) == mode
+        seen.add((mode, img.dtype.name))
+    assert {(0, "uint8"), (1, "uint8"), (0, "float32")} <= seen
+
+
+def test_resize_oracle_identity_and_fma():
+    from oracle.raster import fma32, image_to_sample, resize_to_sample
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (2, 20, 28, 3), dtype=np.uint8)
+    assert np.array_equal(resize_to_sample(img, 20, 28), image_to_sample(img))      # same size: Resize is a copy
+    # fma32 is the exactly rounded fused multiply-add: against exact rational arithmetic on awkward operands
+    from fractions import Fraction
+    a = rng.standard_normal(2000).astype(np.float32)
+    b = rng.standard_normal(2000).astype(np.float32)
+    c = (-(a.astype(np.float64) * b.astype(np.float64))).astype(np.float32) + rng.standard_normal(2000).astype(np.float32) * 1e-7
+    got = fma32(a, b, c)
+    for i in range(0, 2000, 7):
+        exact = Fraction(float(a[i])) * Fraction(float(b[i])) + Fraction(float(c[i]))
+        lo, hi = np.nextafter(got[i], np.float32(-np.inf)), np.nextafter(got[i], np.float32(np.inf))
+        assert abs(Fraction(float(got[i])) - exact) <= min(abs(Fraction(float(lo)) - exact), abs(Fraction(float(hi)) - exact))

@@ -1,9 +1,9 @@
 """CPU plumbing (BASELINE.json configs[0]): the reference's UNMODIFIED `DriveSceneGen/pipeline/training_pipeline.py`
 and `DriveSceneGen/utils/datasets/dataset.py` run against the `diffusers` / `accelerate` shims.
 
-There is no GPU here, so the test-suite plugs the CPU oracle behind the host API through
-`drivescenegen_b200.testing.register_cpu_backend` (test infrastructure; the product never does this).  Skipped where
-/root/reference is absent (the GPU box)."""
+There is no GPU here, so the test-suite monkeypatches the host-API classes to serve CPU tensors from the CPU oracle
+(`tests/cpu_plumbing.py`, test infrastructure; the product has no CPU path and no hook for one).  Skipped where
+/root/reference is absent (the GPU box) — the GPU box runs the staged copies in `tests/test_gpu_reference_scripts.py`."""
 import os
 import sys
 import types
@@ -18,36 +18,10 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "DriveSceneG
 
 
 @pytest.fixture()
-def oracle_backend():
-    from drivescenegen_b200 import testing
-    from oracle.schedulers import OracleDDPMScheduler
-    from oracle.unet import OracleUNet2D
-    cache = {}
-
-    def unet_forward(model, sample, timestep):
-        key = id(model)
-        if key not in cache:
-            cfg = {k: model.config[k] for k in ("sample_size", "in_channels", "out_channels", "down_block_types",
-                                                "up_block_types", "block_out_channels", "layers_per_block",
-                                                "attention_head_dim", "norm_num_groups", "norm_eps", "add_attention")}
-            cache[key] = OracleUNet2D(**cfg)
-        params = dict(model.named_parameters())
-        return torch.func.functional_call(cache[key], params, (sample, timestep))[0]
-
-    def ddpm_step(sched, model_output, t, sample, generator):
-        o = OracleDDPMScheduler()
-        if sched.num_inference_steps:
-            o.set_timesteps(sched.num_inference_steps)
-        return o.step(model_output, t, sample, generator=generator)
-
-    def add_noise(sched, x0, noise, t):
-        return OracleDDPMScheduler().add_noise(x0, noise, t)
-
-    testing.register_cpu_backend("unet_forward", unet_forward)
-    testing.register_cpu_backend("ddpm_step", ddpm_step)
-    testing.register_cpu_backend("add_noise", add_noise)
+def oracle_backend(monkeypatch):
+    import cpu_plumbing
+    cpu_plumbing.install(monkeypatch)
     yield
-    testing.clear_cpu_backends()
 
 
 def test_training_pipeline_runs_unmodified_on_cpu(tmp_path, monkeypatch, oracle_backend):
