@@ -11,8 +11,8 @@ namespace dsg {
 __device__ __forceinline__ float ddpm_one(float e, float x, float z, const float* c) {
   // pred_original_sample = (sample - beta_prod_t**0.5 * model_output) / alpha_prod_t**0.5
   float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c[0], e)), c[1]);
-  // clamp(-r, r)
-  x0 = fminf(fmaxf(x0, -c[5]), c[5]);
+  // clamp(-r, r); torch.clamp propagates NaN (fminf / fmaxf alone would turn a NaN prediction into +-r)
+  x0 = (x0 != x0) ? x0 : fminf(fmaxf(x0, -c[5]), c[5]);
   // pred_prev_sample = coeff_x0 * x0 + coeff_xt * sample
   float p = __fadd_rn(__fmul_rn(c[2], x0), __fmul_rn(c[3], x));
   // + sigma * noise (t > 0)
@@ -21,7 +21,7 @@ __device__ __forceinline__ float ddpm_one(float e, float x, float z, const float
 }
 __device__ __forceinline__ float ddim_one(float e, float x, float z, const float* c) {
   float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c[0], e)), c[1]);
-  x0 = fminf(fmaxf(x0, -c[5]), c[5]);
+  x0 = (x0 != x0) ? x0 : fminf(fmaxf(x0, -c[5]), c[5]);
   // prev = abar_prev**0.5 * x0 + (1 - abar_prev - std^2)**0.5 * eps
   float p = __fadd_rn(__fmul_rn(c[2], x0), __fmul_rn(c[3], e));
   if (c[6] != 0.0f) p = __fadd_rn(p, __fmul_rn(c[4], z));

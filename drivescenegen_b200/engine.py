@@ -455,7 +455,7 @@ class _Program:
                 for k in range(i, j):
                     name, meta = self.op_info[k]
                     ops.append(self.op_sub[k][0](n0, g))
-                    info.append((name, {kk: (v * g // self.b if kk in ("flops", "bytes") else v)
+                    info.append((name, {kk: (v * g // self.b if kk in ("flops", "flops_exec", "bytes") else v)
                                         for kk, v in meta.items()}))
             i = j
         self.ops, self.op_info = ops, info
@@ -591,8 +591,12 @@ class _Program:
         # reference op count: an identity shortcut panel stands for a residual ADD, not for GEMM work
         k_ref = {0: 9 * cin + (csc1 + csc2 if count_sc else 0), 1: 9 * cin, 2: 9 * cin, 3: cin}[mode]
         opx = {0: hw[0] * hw[1], 1: hw[0] * hw[1] // 4, 2: hw[0] * hw[1] * 4, 3: hw[0] * hw[1]}[mode]
+        # executed: the upsample conv runs as 4 sub-pixel phases of 2x2 taps (4/9 of the MACs), an identity shortcut
+        # panel is real GEMM work
+        k_exec = {0: 9 * cin + csc1 + csc2, 1: 9 * cin, 2: 4 * cin, 3: cin}[mode]
         meta = {"mode": mode, "hw": hw, "cin": cin + csc1 + csc2, "cout": cout,
-                "flops": 2 * self.b * opx * cout * k_ref}  # algorithmic (reference op count, no sub-pixel discount)
+                "flops": 2 * self.b * opx * cout * k_ref,   # algorithmic (reference op count, no sub-pixel discount)
+                "flops_exec": 2 * self.b * opx * cout * k_exec}
         sub = None
         if gn_coef is None:
             def sub(n0, ng, a=a):

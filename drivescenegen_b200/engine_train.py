@@ -218,7 +218,7 @@ class TrainProgram(_Program):
             self._colsum_job(colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr,
                              _p(total), None)
         nbytes = b * npx * c * 2
-        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0)},
+        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0), "bytes_alg": 3 * nbytes},
                     lambda st: check(lib.dsg_gn_bwd(*a1, st), "gn_bwd"))
 
     # ------------------------------------------------------------------ the backward program

@@ -377,13 +377,22 @@ class DDPMPipeline:
                     else:
                         gs.z.copy_(randn_tensor(image.shape, generator=generator, device=dev, dtype=image.dtype))
                 gs.advance()
-            return gs.x.clone()
+            return self._finite(gs.x.clone())
         for t in self.progress_bar(sched.timesteps):
             model_output = self.unet(image, t).sample
             if ddim:
                 image = sched.step(model_output, t, image, eta=eta, generator=generator).prev_sample
             else:
                 image = sched.step(model_output, t, image, generator=generator).prev_sample
+        return self._finite(image)
+
+    @staticmethod
+    def _finite(image: torch.Tensor) -> torch.Tensor:
+        """Activations live in HBM as fp16: a badly scaled checkpoint can overflow them.  One reduction over the final
+        latent at the end of the run (the only host read of the loop) turns that into an error instead of NaN images."""
+        if not bool(torch.isfinite(image).all()):
+            raise DsgError("sampling produced non-finite values: activations left the fp16 range inside the U-Net "
+                           "(check the checkpoint's GroupNorm gains / weight scale)")
         return image
 
     @torch.no_grad()

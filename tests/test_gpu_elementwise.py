@@ -119,6 +119,59 @@ def test_add_noise_bit_exact():
     assert e.shape[0] == 0
 
 
+def test_add_noise_out_of_range_timestep_never_reads_out_of_bounds():
+    """upstream: IndexError.  Host-visible timesteps raise; device-resident ones poison that sample with NaN."""
+    from drivescenegen_b200.hostapi import DDPMScheduler
+    s = DDPMScheduler()
+    x0, nz = torch.ones(3, 3, 8, 8, device=_dev()), torch.ones(3, 3, 8, 8, device=_dev())
+    with pytest.raises(IndexError):
+        s.add_noise(x0, nz, torch.tensor([5, 1000, 7]))
+    with pytest.raises(IndexError):
+        s.add_noise(x0, nz, torch.tensor([-1, 0, 7]))
+    got = s.add_noise(x0, nz, torch.tensor([5, 1000, 7], device=_dev()))
+    assert torch.isfinite(got[0]).all() and torch.isnan(got[1]).all() and torch.isfinite(got[2]).all()
+
+
+def test_scheduler_steps_propagate_nan_like_torch_clamp():
+    """torch.clamp keeps NaN; a NaN model output (fp16 overflow inside the U-Net) must not be laundered into +-1."""
+    from drivescenegen_b200 import ops
+    from drivescenegen_b200.hostapi import DDIMScheduler, DDPMScheduler
+    from oracle.schedulers import OracleDDIMScheduler, OracleDDPMScheduler
+    g = torch.Generator().manual_seed(4)
+    eps, x, z = (torch.randn(1, 3, 8, 8, generator=g) for _ in range(3))
+    eps[0, 0, 0, 0] = float("nan")
+    eps[0, 1, 2, 3] = float("inf")
+    sch, osch = DDPMScheduler(), OracleDDPMScheduler()
+    ref = osch.step(eps, 500, x, variance_noise=z)
+    got = ops.ddpm_step(eps.to(_dev()), x.to(_dev()), z.to(_dev()), sch.coef_table(_dev()), 500).cpu()
+    assert torch.isnan(ref[0, 0, 0, 0]) and torch.isnan(got[0, 0, 0, 0])
+    assert torch.equal(torch.isnan(got), torch.isnan(ref)) and torch.equal(got.nan_to_num(0.0), ref.nan_to_num(0.0))
+    dsch, dosch = DDIMScheduler(), OracleDDIMScheduler()
+    dsch.set_timesteps(50)
+    dosch.set_timesteps(50)
+    refd = dosch.step(eps, 500, x)
+    gotd = ops.ddpm_step(eps.to(_dev()), x.to(_dev()), None, dsch.coef_table(_dev()), 500, ddim=True).cpu()
+    assert torch.equal(torch.isnan(gotd), torch.isnan(refd)) and torch.equal(gotd.nan_to_num(0.0), refd.nan_to_num(0.0))
+
+
+def test_step_advance_walks_the_schedule_on_the_device():
+    from drivescenegen_b200 import _lib
+    from drivescenegen_b200._lib import check
+    lib = _lib.load()
+    sched = torch.tensor([980, 960, 3, 0], dtype=torch.int32, device=_dev())
+    state = torch.tensor([0, 4], dtype=torch.int32, device=_dev())
+    t_f = torch.zeros(5, device=_dev())
+    row = torch.zeros(1, dtype=torch.int32, device=_dev())
+    st = torch.cuda.current_stream().cuda_stream
+    seen = []
+    for _ in range(6):   # two calls past the end stay on the last entry
+        check(lib.dsg_step_advance(sched.data_ptr(), state.data_ptr(), t_f.data_ptr(), 5, row.data_ptr(), st), "advance")
+        seen.append((int(row.item()), t_f.tolist(), int(state[0].item())))
+    assert [s[0] for s in seen] == [980, 960, 3, 0, 0, 0]
+    assert all(s[1] == [float(s[0])] * 5 for s in seen)
+    assert [s[2] for s in seen] == [1, 2, 3, 4, 5, 6]
+
+
 def test_latent_to_image_exact():
     from drivescenegen_b200 import ops
     g = torch.Generator().manual_seed(9)

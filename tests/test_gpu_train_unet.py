@@ -1,6 +1,9 @@
 """GPU parity of the whole training path: UNet2DModel forward + hand-written backward vs the CPU oracle under torch
 autograd (fp32).  Tolerance (fp16 operands / activations / activation gradients, fp32 accumulation): relative L2 error of
-each parameter gradient <= 4e-2, of all gradients together <= 2e-2, of the output <= 1e-2."""
+each parameter gradient <= 1e-2, of all gradients together <= 5e-3, of the output <= 3e-3 (measured on B200: worst single
+gradient ~4e-3, all together ~2e-3, output ~1e-3), up to the benchmarked 256x256 resolution."""
+import sys
+
 import pytest
 import torch
 
@@ -36,7 +39,8 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("name,cfg,size,batch", [("c1", CFG_C1, 64, 2), ("ref", CFG_REF, 64, 2), ("ref128", CFG_REF, 128, 1)])
+@pytest.mark.parametrize("name,cfg,size,batch", [("c1", CFG_C1, 64, 2), ("ref", CFG_REF, 64, 2), ("ref128", CFG_REF, 128, 1),
+                                                 ("ref256", CFG_REF, 256, 1)])
 def test_unet_backward_matches_oracle_autograd(name, cfg, size, batch):
     oracle, model = _pair(cfg)
     g = torch.Generator().manual_seed(5)
@@ -50,7 +54,8 @@ def test_unet_backward_matches_oracle_autograd(name, cfg, size, batch):
     assert out.requires_grad
     loss = torch.nn.functional.mse_loss(out, target.to(_dev()))
     loss.backward()
-    assert _rel(out.detach().cpu(), ref_out.detach()) < 1e-2
+    rel_out = _rel(out.detach().cpu(), ref_out.detach())
+    assert rel_out < 3e-3, rel_out
     ref = dict(oracle.named_parameters())
     num = den = 0.0
     worst = []
@@ -67,8 +72,10 @@ def test_unet_backward_matches_oracle_autograd(name, cfg, size, batch):
             continue
         worst.append((_rel(gg, gr), n))
     worst.sort(reverse=True)
-    assert (num / den) ** 0.5 < 2e-2, ((num / den) ** 0.5, worst[:5])
-    assert worst[0][0] < 4e-2, worst[:8]
+    print(f"[parity] backward {name} {size}x{size} b={batch}: out rel_l2={rel_out:.2e} all-grads rel_l2="
+          f"{(num / den) ** 0.5:.2e} worst grad {worst[0][1]} {worst[0][0]:.2e}", file=sys.stderr)
+    assert (num / den) ** 0.5 < 5e-3, ((num / den) ** 0.5, worst[:5])
+    assert worst[0][0] < 1e-2, worst[:8]
 
 
 def test_unet_backward_no_loss_scale_and_large_loss_scale_agree():

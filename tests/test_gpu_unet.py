@@ -3,7 +3,9 @@
 Tolerance (stated per BASELINE.json north_star): the engine computes with fp16 operands and fp32 accumulation
 (the reference's own `mixed_precision="fp16"` numerics, DriveSceneGen/scripts/train.py:24) while the oracle is pure
 fp32, so outputs agree to fp16 rounding accumulated over ~60 layers:
-    relative L2 error  <= 1e-2      and      max |err| <= 5e-2 * max |ref|.
+    relative L2 error  <= 3e-3      and      max |err| <= 1.5e-2 * max |ref|
+(measured on B200: 1.0e-3 .. 1.3e-3 and 3e-3 .. 6e-3; a regression that triples the error fails).  Multi-step sampling
+compounds the per-step error: the trajectory tests bound its growth step by step.
 """
 import os
 import sys
@@ -13,8 +15,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-REL_L2_TOL = 1e-2
-MAX_TOL = 5e-2
+REL_L2_TOL = 3e-3
+MAX_TOL = 1.5e-2
 
 REF_CFG = dict(sample_size=(256, 256), in_channels=3, out_channels=3, layers_per_block=2,
                block_out_channels=(64, 128, 256, 512), down_block_types=("DownBlock2D",) * 4,
@@ -86,6 +88,123 @@ def test_reference_config_forward(hw, batch):
         ref = oracle(x, t)[0]
         got = model(x.cuda(), t.cuda()).sample
     _check(got, ref, f"ref-config {hw} b={batch}")
+
+
+def test_reference_config_forward_at_the_benchmarked_batch():
+    """BASELINE configs[1] shape: 256x256, B = 16 — the program bench.py times (persistent-CTA tile assignment, statistics
+    flush order and the L2 sample-group schedule all depend on the batch), per-sample timesteps, every sample checked."""
+    oracle, model = _pair(REF_CFG)
+    x = torch.randn(16, 3, 256, 256, generator=torch.manual_seed(1234))
+    t = torch.tensor([999, 3, 500, 250, 750, 0, 998, 1, 100, 900, 333, 666, 42, 640, 17, 871], dtype=torch.long)
+    with torch.no_grad():
+        ref = oracle(x, t)[0]
+        got = model(x.cuda(), t.cuda()).sample
+    _check(got, ref, "ref-config 256x256 b=16")
+    worst = max(_errs(got[i], ref[i])[0] for i in range(16))
+    print(f"[parity] worst single-sample rel_l2 at b=16: {worst:.3e}", file=sys.stderr)
+    assert worst <= REL_L2_TOL
+    # the same samples one at a time through the B = 1 program: a different tile schedule, the same function
+    with torch.no_grad():
+        one = torch.cat([model(x[i:i + 1].cuda(), t[i:i + 1].cuda()).sample for i in (0, 7, 15)])
+    assert _errs(one, got[[0, 7, 15]].cpu())[0] < 1e-3
+
+
+def test_ten_step_trajectory_with_shared_noise_at_256():
+    """parity on the first 10 DDPM steps at 256x256 with shared noise (B = 2 keeps the CPU side at a
+    few seconds).  The engine runs its CUDA-graph session; the oracle runs the plain loop; both consume the same initial
+    latent and the same per-step variance noise.  Per-step relative L2 of the sample is printed and bounded: the error
+    may grow (each step feeds the next) but must stay within 4x the single-step tolerance over 10 steps."""
+    from drivescenegen_b200.hostapi import DDPMScheduler, DenoiseSession
+    from oracle.schedulers import OracleDDPMScheduler
+    oracle, model = _pair(REF_CFG)
+    sched, osched = DDPMScheduler(), OracleDDPMScheduler()
+    sched.set_timesteps(1000)
+    osched.set_timesteps(1000)
+    g = torch.manual_seed(4321)
+    x0 = torch.randn(2, 3, 256, 256, generator=g)
+    noise = [torch.randn(2, 3, 256, 256, generator=g) for _ in range(10)]
+    ts = [int(t) for t in sched.timesteps[:10]]
+    sess = DenoiseSession(model, sched, (2, 3, 256, 256))
+    sess.load(x0.cuda())
+    sess.begin(ts)
+    x_ref = x0.clone()
+    rels = []
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            eps = oracle(x_ref, t)[0]
+            x_ref = osched.step(eps, t, x_ref, variance_noise=noise[i])
+            got = sess.advance(noise[i].cuda()).cpu()
+            rels.append(((got - x_ref).norm() / x_ref.norm()).item())
+    print("[parity] 10-step trajectory rel_l2 per step: " + " ".join(f"{r:.2e}" for r in rels), file=sys.stderr)
+    assert all(torch.isfinite(torch.tensor(rels)))
+    assert rels[0] <= REL_L2_TOL
+    assert max(rels) <= 4 * REL_L2_TOL
+    # late steps of the schedule too (small t: the x0 clamp is active and sigma is small) — 5 steps ending at t = 0
+    ts2 = [4, 3, 2, 1, 0]
+    sess.load(x0.cuda())
+    sess.begin(ts2)
+    x_ref = x0.clone()
+    with torch.no_grad():
+        for i, t in enumerate(ts2):
+            x_ref = osched.step(oracle(x_ref, t)[0], t, x_ref, variance_noise=noise[i])
+            got = sess.advance(noise[i].cuda()).cpu()
+    r = ((got - x_ref).norm() / x_ref.norm()).item()
+    print(f"[parity] 5 steps ending at t=0: rel_l2 {r:.2e}", file=sys.stderr)
+    assert r <= 4 * REL_L2_TOL
+
+
+def test_stress_large_groupnorm_gains_and_wide_activations():
+    """fp16 activations in HBM: GroupNorm gains x8 (a trained-like, badly scaled checkpoint) and inputs 4x wider than
+    N(0,1) drive the conv outputs far from unit scale.  The output must stay finite and within 3x the usual tolerance
+    of the fp32 oracle — and when activations DO leave the fp16 range the sampling path reports it instead of returning
+    NaN images."""
+    from drivescenegen_b200._lib import DsgError
+    from drivescenegen_b200.hostapi import DDPMPipeline, DDPMScheduler
+    oracle, model = _pair(C1_CFG)
+    with torch.no_grad():
+        for name, p in oracle.named_parameters():
+            if "norm" in name and name.endswith("weight"):
+                p.mul_(8.0)
+    model.load_state_dict(oracle.state_dict())
+    model = model.to("cuda:0").eval()
+    x = 4.0 * torch.randn(2, 3, 64, 64, generator=torch.manual_seed(77))
+    with torch.no_grad():
+        ref = oracle(x, 500)[0]
+        got = model(x.cuda(), 500).sample
+    rel, mx = _errs(got, ref)
+    print(f"[parity] stress gn x8, input x4: |ref|max={ref.abs().max():.1f} rel_l2={rel:.3e} max_rel={mx:.3e}",
+          file=sys.stderr)
+    assert torch.isfinite(got).all() and rel <= 3 * REL_L2_TOL
+    # overflow: gains large enough to push activations past 65504 -> inf/nan inside the U-Net
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if "norm" in name and name.endswith("weight"):
+                p.mul_(1e4)
+    pipe = DDPMPipeline(unet=model, scheduler=DDPMScheduler())
+    pipe.set_progress_bar_config(disable=True)
+    with pytest.raises(DsgError, match="non-finite"):
+        pipe(batch_size=1, generator=torch.manual_seed(1), num_inference_steps=2, output_type="np.array")
+
+
+def test_ddpm_pipeline_with_a_ddim_scheduler_graph_equals_eager():
+    """DDPMPipeline(unet, DDIMScheduler()) is legal upstream and means DDIM (eta = 0) steps; the CUDA-graph path
+    must pick the step kernel from the scheduler's type exactly like the eager path does."""
+    from drivescenegen_b200.hostapi import DDIMPipeline, DDIMScheduler, DDPMPipeline, DenoiseSession
+    _, model = _pair(C1_CFG)
+    pipe = DDPMPipeline(unet=model, scheduler=DDIMScheduler())
+    pipe.set_progress_bar_config(disable=True)
+    outs = {}
+    for use_graph in (True, False):
+        pipe.use_cuda_graph = use_graph
+        outs[use_graph] = pipe(batch_size=2, generator=torch.manual_seed(3), num_inference_steps=5,
+                               output_type="np.array", return_dict=False)[0]
+    assert (outs[True] == outs[False]).all()
+    ddim = DDIMPipeline(unet=model, scheduler=DDIMScheduler())
+    ddim.set_progress_bar_config(disable=True)
+    ref = ddim(batch_size=2, generator=torch.manual_seed(3), num_inference_steps=5, output_type="np.array").images
+    assert (outs[True] == ref).all()
+    with pytest.raises(ValueError):
+        DenoiseSession(model, DDIMScheduler(), (1, 3, 64, 64), ddim=False)
 
 
 def test_attention_blocks_config_forward():
