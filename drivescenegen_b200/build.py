@@ -37,6 +37,35 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(out_path: str, defines, verbose: bool = False) -> str:
+    """A/B builds: the same sources with extra -D macros into a separate .so (swapped in on the GPU box by the A/B
+    stage of tools/gpu.sh); objects go to their own directory so the default build's stamp stays valid."""
+    obj_dir = OBJ + "_variant"
+    os.makedirs(obj_dir, exist_ok=True)
+    extra = [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src[:-3] + ".o")
+        r = subprocess.run([NVCC, *ARCH, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj],
+                           capture_output=True, text=True)
+        return src, obj, r
+
+    objs = []
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for src, obj, r in ex.map(compile_one, _sources()):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(f"--- {src}\n{r.stdout}{r.stderr}\n")
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}")
+            objs.append(obj)
+    r = subprocess.run([NVCC, *ARCH, "-shared", "-o", out_path, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return out_path
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
@@ -70,4 +99,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--variant" in sys.argv:   # python -m drivescenegen_b200.build --variant out.bin -DNAME=VALUE ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

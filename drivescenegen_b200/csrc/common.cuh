@@ -222,6 +222,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store: one box from shared memory (written by the generic proxy, then fence_proxy_async) to a 4-D tensor; elements
+// outside the tensor's extents are clipped by the TMA unit.  Tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk group of this thread has finished READING its shared-memory source (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // One elected lane of a fully converged warp.  Warp-specialised roles run WARP-UNIFORM (all 32 lanes execute the
 // loop with identical values) and only the TMA / tcgen05 instructions sit under this predicate: operands computed in
 // uniform control flow live in uniform registers, so UTMALDG / UTCHMMA issue back to back.  Computing them under an

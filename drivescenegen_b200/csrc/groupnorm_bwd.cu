@@ -9,8 +9,10 @@
 //   m1_g     = sum_{c in g} gamma_c A_c / count                  m2_g = sum_{c in g} gamma_c B_c / count
 //   dx       = rstd_g * (gamma_c * g - m1_g - xh * m2_g)
 // Two streaming passes: gn_bwd_stats_kernel (reads da, x) writes per-(sample, pixel-chunk, channel) partials of A and B
-// in a fixed layout; gn_bwd_apply_kernel (reads da, x again) sums the chunk partials in a fixed order — deterministic,
-// no atomics — and writes dx, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
+// in a fixed layout and — when there is an activation — stores g over da IN PLACE (da is scratch: the dgrad conv that
+// produced it is its only writer and this backward its only reader), so the SiLU derivative (one MUFU + the fp16x2
+// arithmetic around it) is evaluated once per element, not once per pass; gn_bwd_apply_kernel (reads g, x) sums the chunk
+// partials in a fixed order — deterministic, no atomics — and writes dx with three FMAs per element, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
 // content of the destination: a tensor with two consumers), split over the two concatenated sources.  It can also emit
 // per-CTA column sums of what it wrote (the time-embedding / conv1-bias gradient of a ResnetBlock).
 // Forward statistics come from the same int64 per-channel totals the forward used (groupnorm.cu).
@@ -25,7 +27,7 @@ constexpr int GB_MAX_C = 2048;
 constexpr int GB_MAX_CHUNKS = 64;
 
 struct GnBwdArgs {
-  const __half* dy;   // [n][hw][C] incoming gradient (w.r.t. the activated, normalised tensor)
+  __half* dy;         // [n][hw][C] incoming gradient (w.r.t. the activated, normalised tensor); act != 0: overwritten by g
   const __half* x1; int c1; const long long* st1;
   const __half* x2; int c2; const long long* st2;
   const float* gamma; const float* beta;
@@ -78,9 +80,24 @@ __device__ __forceinline__ float silu_grad_f(float y) {
   return sg * fmaf(y, 1.0f - sg, 1.0f);
 }
 
+// The same for two elements in fp16x2, given h = y / 2 (already rounded to fp16): ONE MUFU op per pair and four fp16x2
+// instructions.  t = tanh(h); sigmoid = (1 + t) / 2; d/dy silu = sigmoid * (1 + y (1 - sigmoid)) = sigmoid * (1 + h (1 - t)).
+// tanh.approx.f16x2 has the same ~2^-11 absolute error near |t| = 1 as tanh.approx.f32, which is what bounds the
+// accuracy of either form.
+__device__ __forceinline__ __half2 silu_grad_h2(__half2 h) {
+  uint32_t hi = *reinterpret_cast<uint32_t*>(&h), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(hi));
+  const __half2 t = *reinterpret_cast<__half2*>(&ti);
+  const __half2 one = __float2half2_rn(1.0f), half_ = __float2half2_rn(0.5f);
+  const __half2 sg = __hfma2(half_, t, half_);
+  const __half2 w = __hfma2(h, __hsub2(one, t), one);
+  return __hmul2(sg, w);
+}
+
 // Pass 1.  Per (sample, pixel chunk, channel): sum g and sum g * x (raw x: the centring is applied when the chunks are
 // combined, sum g * xh = rstd * (sum g x - mean * sum g), which keeps the per-thread state small).
 constexpr int GB_ILP = 4;
+template <bool ACT>
 __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwdArgs a) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
@@ -100,14 +117,17 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   if (p_end > a.hw) p_end = a.hw;
   int64_t p = p_begin + prow;
   pdl_sync();
-  gn_moments(a, n, s_mean, s_rstd, s_t);
+  if (ACT) gn_moments(a, n, s_mean, s_rstd, s_t);
   if (active) {
-    float ga[8], yb[8], sA[8], sB[8];
+    float gah[8], ybh[8], sA[8], sB[8];   // y / 2 = x * gah + ybh
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int ch = ch0 + j, g = ch / cpg;
-      ga[j] = a.gamma[ch] * s_rstd[g];
-      yb[j] = a.beta[ch] - s_mean[g] * ga[j];
+      if (ACT) {
+        const int ch = ch0 + j, g = ch / cpg;
+        const float ga = a.gamma[ch] * s_rstd[g];
+        gah[j] = 0.5f * ga;
+        ybh[j] = 0.5f * (a.beta[ch] - s_mean[g] * ga);
+      }
       sA[j] = 0.f; sB[j] = 0.f;
     }
     // GB_ILP pixels per iteration: all loads of an iteration are issued before the first use; two resident CTAs per SM
@@ -119,20 +139,33 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
         const int64_t pp = p + (int64_t)u * ppi;
         if (pp < p_end) {
           rx[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
-          rd[u] = ldg_nc_v4(a.dy + (base_px + pp) * C + ch0);
+          // da is rewritten below by this same thread: plain (coherent) load, not the read-only path
+          rd[u] = *reinterpret_cast<const uint4*>(a.dy + (base_px + pp) * C + ch0);
         }
       }
 #pragma unroll
       for (int u = 0; u < GB_ILP; ++u) {
-        if (p + (int64_t)u * ppi < p_end) {
-          float fx[8], fd[8];
-          unpack8(rx[u], fx); unpack8(rd[u], fd);
+        const int64_t pp = p + (int64_t)u * ppi;
+        if (pp < p_end) {
+          const __half2* hx = reinterpret_cast<const __half2*>(&rx[u]);
+          __half2* hd = reinterpret_cast<__half2*>(&rd[u]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
-            sA[j] += g;
-            sB[j] = fmaf(g, fx[j], sB[j]);
+          for (int k = 0; k < 4; ++k) {
+            const float2 fx = __half22float2(hx[k]);
+            __half2 g2 = hd[k];
+            if (ACT) {
+              const __half2 h2 = __floats2half2_rn(fmaf(fx.x, gah[2 * k], ybh[2 * k]),
+                                                   fmaf(fx.y, gah[2 * k + 1], ybh[2 * k + 1]));
+              g2 = __hmul2(g2, silu_grad_h2(h2));
+              hd[k] = g2;
+            }
+            const float2 g = __half22float2(g2);   // the sums see exactly the g the second pass reads
+            sA[2 * k] += g.x;
+            sA[2 * k + 1] += g.y;
+            sB[2 * k] = fmaf(g.x, fx.x, sB[2 * k]);
+            sB[2 * k + 1] = fmaf(g.y, fx.y, sB[2 * k + 1]);
           }
+          if (ACT) stg_v4(a.dy + (base_px + pp) * C + ch0, rd[u]);
         }
       }
     }
@@ -154,8 +187,15 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   }
 }
 
-// Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1).
-__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwdArgs a) {
+// Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1); g is what pass 1
+// left in a.dy.
+#ifndef GB_APPLY_CTAS
+#define GB_APPLY_CTAS 2
+#endif
+#ifndef GB_APPLY_ILP
+#define GB_APPLY_ILP 2
+#endif
+__global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
   const int n = blockIdx.y;
@@ -174,7 +214,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   const int64_t p_begin = (int64_t)blockIdx.x * a.px_per_block;
   int64_t p_end = p_begin + a.px_per_block;
   if (p_end > a.hw) p_end = a.hw;
-  constexpr int ILP = 2;
+  constexpr int ILP = GB_APPLY_ILP;
   int64_t p = p_begin + prow;
   const bool want_osum = (from1 ? a.osum1 : a.osum2) != nullptr;
   pdl_sync();
@@ -210,13 +250,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs_acc[j] = 0.f; os_acc[j] = 0.f; }
   if (active) {
-    float ga[8], yb[8], pc[8], qc[8];
+    float ga[8], pc[8], qc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = ch0 + j, g = ch / cpg;
       const float mu = s_mean[g], rs = s_rstd[g];
       ga[j] = a.gamma[ch] * rs;
-      yb[j] = a.beta[ch] - mu * ga[j];
       pc[j] = -rs * rs * s_m2[g];
       qc[j] = rs * (mu * rs * s_m2[g] - s_m1[g]);
     }
@@ -241,8 +280,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
           unpack8(rx[u], fx); unpack8(rd[u], fd); unpack8(ra[u], fa); unpack8(ro[u], fo);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float g = a.act ? fd[j] * silu_grad_f(fmaf(fx[j], ga[j], yb[j])) : fd[j];
-            const float d = fmaf(ga[j], g, fmaf(pc[j], fx[j], qc[j]));
+            const float d = fmaf(ga[j], fd[j], fmaf(pc[j], fx[j], qc[j]));
             cs_acc[j] += d;
             r[j] = (d + fa[j]) + fo[j];
           }
@@ -355,7 +393,7 @@ using namespace dsg;
 
 extern "C" {
 
-int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
+int dsg_gn_bwd(void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
                float* osum1, float* osum2, int32_t parts, int32_t n, int64_t hw, int32_t groups, void* stream) {
@@ -376,7 +414,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
                 "dsg_gn_bwd: unaligned pointer");
   if (n == 0) return DSG_OK;
   GnBwdArgs a;
-  a.dy = (const __half*)dy;
+  a.dy = (__half*)dy;
   a.x1 = (const __half*)x1; a.c1 = c1; a.st1 = (const long long*)stats1;
   a.x2 = (const __half*)x2; a.c2 = c2; a.st2 = (const long long*)stats2;
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.act = act;
@@ -388,7 +426,10 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   a.inv_cnt_q = 1.0 / 1048576.0 / ((double)hw * (double)(C / groups));
   cudaStream_t st = (cudaStream_t)stream;
   a.px_per_block = ceil_div64(hw, chunks);
-  launch_k(gn_bwd_stats_kernel, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
+  if (act)
+    launch_k(gn_bwd_stats_kernel<true>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
+  else
+    launch_k(gn_bwd_stats_kernel<false>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
   int64_t ctas = parts;
   if (ctas == 0) {

@@ -129,6 +129,110 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
   }
 }
 
+// The same tile through shared memory + TMA stores (BLOCK_N = 64): with one pixel per lane a direct STG.128 touches 32
+// different 128-byte lines with 16 bytes each — every 32-byte sector is written twice and the LSU store path, not the
+// tensor pipe, paces the cout = 64 layers.  Here each warp parks its 32 pixels x 64 channels of every accumulator (4 KB
+// each, 16-byte chunks XOR-swizzled with the pixel index so the STS.128s are conflict-free = the TMA unit's SWIZZLE_128B
+// pattern) in its own staging buffers and one elected lane issues ONE tensor store per accumulator (box = 64 channels x
+// TW pixels x 32 / TW rows) once its second 32-channel slice is staged; rows / columns outside the image are clipped by
+// the TMA unit.  `pending`: stores of this warp's previous tile may still be reading the staging buffers.
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void epi_tile_tma(uint32_t taddr, const float* sb, const bool (&valid)[MT],
+                                             const int64_t (&off)[MT], const __half* res, float* sstat_warp, int lane,
+                                             uint8_t* stage_warp /* [MT][4 KB] */, const CUtensorMap* omap, int c0,
+                                             int w0, const int (&hrow)[MT], int n, bool& pending) {
+  static_assert(BLOCK_N == 64, "one 128-byte swizzle span per pixel row");
+  constexpr int NCH = BLOCK_N / 32, NIT = NCH * MT;
+  uint32_t v[2][32];
+  uint4 rn[2][4];
+#pragma unroll
+  for (int pre = 0; pre < 2; ++pre) {
+    if (pre < NIT) {
+      const int pc = pre / MT, pm = pre % MT;
+      if (res && valid[pm]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rn[pre][j] = ldg_nc_v4(res + off[pm] + pc * 32 + j * 8);
+      }
+    }
+  }
+  tmem_ld_32x32(taddr, v[0]);
+  if (pending) {  // the previous tile's stores have had a whole main loop to drain the staging buffers
+    if (lane == 0) bulk_wait_group_read0();
+    __syncwarp();
+    pending = false;
+  }
+  float a1[16], a2[16];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int c = it / MT, m = it % MT;
+    tmem_ld_wait();
+    if (it + 1 < NIT) {
+      const int nc = (it + 1) / MT, nm = (it + 1) % MT;
+      tmem_ld_32x32(taddr + (uint32_t)(nm * BLOCK_N + nc * 32), v[(it + 1) & 1]);
+    }
+    uint4 rc[4];
+    if (res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rc[j] = rn[it & 1][j];
+      if (it + 2 < NIT) {
+        const int nc = (it + 2) / MT, nm = (it + 2) % MT;
+        if (valid[nm]) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rn[it & 1][j] = ldg_nc_v4(res + off[nm] + nc * 32 + j * 8);
+        }
+      }
+    }
+    float f[32];
+    if (valid[m]) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + j);
+        f[j] = __uint_as_float(v[it & 1][j]) + b4.x;
+        f[j + 1] = __uint_as_float(v[it & 1][j + 1]) + b4.y;
+        f[j + 2] = __uint_as_float(v[it & 1][j + 2]) + b4.z;
+        f[j + 3] = __uint_as_float(v[it & 1][j + 3]) + b4.w;
+      }
+      if (res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float r[8];
+          unpack8(rc[j], r);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) f[j * 8 + u] += r[u];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 0.f;  // rows outside the image count as nothing (and are clipped by the store)
+    }
+    if (sstat_warp) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x0 = f[2 * j], x1 = f[2 * j + 1];
+        const float s = x0 + x1, qq = fmaf(x0, x0, x1 * x1);
+        if (m == 0) { a1[j] = s; a2[j] = qq; } else { a1[j] += s; a2[j] += qq; }
+      }
+      if (m == MT - 1) {
+        warp_pairsum16x2(a1, a2, lane);
+        if (!(lane & 1)) reinterpret_cast<float2*>(sstat_warp)[c * 16 + (lane >> 1)] = make_float2(a1[0], a2[0]);
+      }
+    }
+    uint8_t* buf = stage_warp + m * 4096 + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(buf + (((c * 4 + j) ^ (lane & 7)) << 4)) = pack8(f + j * 8);
+    if (c == NCH - 1) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(omap, stage_warp + m * 4096, c0, w0, hrow[m], n);
+        bulk_commit_group();
+      }
+      pending = true;
+    }
+  }
+}
+
 // combine the four warps' pair totals of one tile (fixed order), convert to the exact fixed-point form and keep them in
 // registers (entry idx is always handled by the same thread); the int64 atomics on the tensor's totals are issued only
 // when the CTA moves on to another (sample, channel block) or runs out of tiles.  Integer adds: the totals are bit-identical
@@ -148,13 +252,15 @@ struct EpiStatsAcc {
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int idx = te + k * 128;
-        if (idx < BLOCK_N && v[k] != 0)
+        if (idx < BLOCK_N && te < 128 && v[k] != 0)
           atomicAdd(reinterpret_cast<unsigned long long*>(dst + (idx >> 1) * 4 + (idx & 1)), (unsigned long long)v[k]);
         v[k] = 0;
       }
     }
   }
-  __device__ __forceinline__ void add_tile(const float* sstat /* [4][BLOCK_N / 2][2] */, int te, long long* stats_nc) {
+  // NW = epilogue warps that parked pair totals for this tile (4, or 8 when two warps share a TMEM lane quadrant)
+  template <int NW = 4>
+  __device__ __forceinline__ void add_tile(const float* sstat /* [NW][BLOCK_N / 2][2] */, int te, long long* stats_nc) {
     if (stats_nc != dst) {
       emit(te);
       dst = stats_nc;
@@ -162,8 +268,10 @@ struct EpiStatsAcc {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int idx = te + k * 128;
-      if (idx < BLOCK_N) {
-        const float t = ((sstat[idx] + sstat[BLOCK_N + idx]) + sstat[2 * BLOCK_N + idx]) + sstat[3 * BLOCK_N + idx];
+      if (idx < BLOCK_N && te < 128) {
+        float t = ((sstat[idx] + sstat[BLOCK_N + idx]) + sstat[2 * BLOCK_N + idx]) + sstat[3 * BLOCK_N + idx];
+        if constexpr (NW == 8)
+          t += ((sstat[4 * BLOCK_N + idx] + sstat[5 * BLOCK_N + idx]) + sstat[6 * BLOCK_N + idx]) + sstat[7 * BLOCK_N + idx];
         v[k] += (idx & 1) ? gn_fix_sq(t) : gn_fix_sum(t);
       }
     }

@@ -20,6 +20,7 @@
 namespace dsg {
 
 constexpr int HL_THREADS = 192;
+constexpr int HL_THREADS_TMA = 320;    // FUSE = 2: eight epilogue warps (two per TMEM lane quadrant, one accumulator each)
 constexpr int HL_THREADS_FUSED = 256;  // + two GroupNorm/SiLU transform warps (256 threads keep 255 registers each)
 constexpr int HL_XF_THREADS = 64;
 constexpr int HL_MAX_GROUPS = 8;
@@ -57,30 +58,36 @@ struct HlPlan {
   const float2* coef;  // fused GroupNorm + SiLU of the input: [N][cin_main] (a / 2, b / 2); act = h + h tanh(h), h = a x / 2 + b / 2
   int cin_main;        // channels of the (concatenated) 3x3 input
   int IH, IW;          // extents of the 3x3 input (masking of the zero padding under the fused transform)
+  int tma_out;         // the fp16 NHWC output goes through the staging buffers + TMA stores (maps.o)
   int64_t total_tiles;
 };
 
 struct alignas(64) HlMaps {
   CUtensorMap a[HL_MAX_MAPS];
   CUtensorMap b;
+  CUtensorMap o;       // output tensor (tma_out only): box = 64 channels x TW pixels x 32 / TW rows, SWIZZLE_128B
 };
 
 // CG = CTAs per MMA: 1, or 2 for tcgen05 cta_group::2 — a cluster of two CTAs shares every MMA (M = 256): each CTA
 // feeds its own 128 pixel rows of A but only HALF of the weight tile, which halves the per-SM shared-memory reads of
 // B.  The UMMA operand fetch tops out near 76 B/clk/SM (tools/umma_probe.cu), which caps a lone CTA at 76 % / 60 %
 // of the tensor peak for N = 256 / 128; the CTA pair lifts that to ~100 % / 80 %.
-template <int BLOCK_N, int MT, int CG>
+template <int BLOCK_N, int MT, int CG, bool STG = false>
 struct HlCfg {
   static constexpr int A_SLOT = MT * 16384 + 4096;  // (MT*8 + 2) rows x 16 px x 128 B (the TW = 8 box is smaller)
   static constexpr int B_ROWS = BLOCK_N / CG;       // weight rows this CTA loads per tap
   static constexpr int B_SLOT = B_ROWS * 128;
   static constexpr int NA = BLOCK_N == 128 ? 3 : 4;
-  static constexpr int NB = CG == 2 ? (BLOCK_N == 256 ? 8 : 12)
+  static constexpr int NB = CG == 2 ? (BLOCK_N == 256 ? 8 : (STG ? 11 : 12))
                                     : (BLOCK_N == 16 ? 12 : (BLOCK_N == 64 ? 9 : (BLOCK_N == 128 ? 7 : 4)));
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int RING_BYTES = NA * A_SLOT + NB * B_SLOT;
+  // epilogue staging for the TMA-store form (cout = 64 layers, CTA pairs): 4 KB per epilogue warp and accumulator
+  static constexpr bool STAGE = STG;
+  static_assert(!STG || (BLOCK_N == 64 && CG == 2), "staging buffers are sized for the BLOCK_N = 64 CTA-pair form");
+  static constexpr int STAGE_BYTES = STAGE ? 4 * MT * 4096 : 0;
   static constexpr int SMEM_BYTES =
-      RING_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
+      RING_BYTES + STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + (STG ? 8 : 4) * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
   static_assert(3 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
@@ -174,22 +181,27 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// FUSE = 2: no input transform; the epilogue stages the fp16 tile in shared memory and writes it with TMA tensor stores
+// (epi_tile_tma, igemm_common.cuh) — BLOCK_N = 64 CTA pairs only.
 // FUSE = 1: the GroupNorm + SiLU that precedes the conv (ResnetBlock2D norm1/norm2 + nonlinearity, conv_norm_out +
 // conv_act) is applied to the activation boxes IN SHARED MEMORY by four extra warps between the TMA landing and the
 // MMA reading (per-(sample, channel) coefficients from dsg_gn_coef, packed half2 math, padding left at zero): the
 // normalised tensor never exists in HBM — one read + one write of every activation less per GroupNorm.
 template <int BLOCK_N, int MT, int CG, int FUSE>
-__global__ void __launch_bounds__(FUSE ? HL_THREADS_FUSED : HL_THREADS, 1)
+__global__ void __launch_bounds__(FUSE == 1 ? HL_THREADS_FUSED : (FUSE == 2 ? HL_THREADS_TMA : HL_THREADS), 1)
 igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ HlPlan p) {
-  using Cfg = HlCfg<BLOCK_N, MT, CG>;
+  using Cfg = HlCfg<BLOCK_N, MT, CG, FUSE == 2>;
   constexpr int NA = Cfg::NA, NB = Cfg::NB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + NA * Cfg::A_SLOT;
-  float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);  // [2][BLOCK_N]
-  float* sstat = sbias + 2 * BLOCK_N;                               // [4][BLOCK_N / 2][2]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 4 * BLOCK_N);
+  uint8_t* stage = smem + Cfg::RING_BYTES;                          // [4 warps][MT][4 KB], 1024-byte aligned
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  constexpr int EW = FUSE == 2 ? 8 : 4;                             // epilogue warps
+  constexpr int EPI_THREADS = EW * 32;
+  float* sstat = sbias + 2 * BLOCK_N;                               // [EW][BLOCK_N / 2][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + EW * BLOCK_N);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NA;
   uint64_t* b_full = a_empty + NA;
@@ -207,6 +219,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < HL_MAX_MAPS; ++i) tma_prefetch_desc(&maps.a[i]);
     tma_prefetch_desc(&maps.b);
+    if (p.tma_out) tma_prefetch_desc(&maps.o);
   }
   // CTA pair (CG = 2): rank 0 is the leader — it owns the "full" barriers (both producers report to them), issues
   // every MMA and collects both epilogues' "accumulator drained" arrivals; "empty"/"accumulator full" barriers
@@ -216,8 +229,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], CG); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], CG); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
-    if constexpr (FUSE != 0)
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EW * CG); }
+    if constexpr (FUSE == 1)
       for (int i = 0; i < NA; ++i) mbar_init(&a_land[i], 1);
     mbar_fence_init();
   }
@@ -245,7 +258,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
           const int wx = tc.w0 + G.dx + tc.pb, hy = tc.h0 + G.dy0 + tc.pa;
           for (int c = 0; c < G.nchunks; ++c) {
             mbar_wait(&a_empty[as], aph ^ 1);
-            if (FUSE != 0 && G.transform) {
+            if (FUSE == 1 && G.transform) {
               // raw box -> this CTA's own "landed" barrier; the transform warps publish it to the MMA issuer
               if (elect_one_sync()) {
                 mbar_arrive_expect_tx(&a_land[as], (uint32_t)G.bytes);
@@ -341,7 +354,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
       }
     }
-  } else if (FUSE != 0 && warp >= 6) {
+  } else if (FUSE == 1 && warp >= 6) {
     // ===================================================== GroupNorm + SiLU transform warps (FUSE only)
     // A box is [pixel][64 channels] in 128-byte rows, 16-byte chunks XOR-swizzled with (pixel & 7).  Thread tt walks the
     // chunks tt, tt + 64, ...: its pixel index advances by 8 each step, so it always meets the SAME logical channel
@@ -414,11 +427,12 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
     int acc = 0; uint32_t acc_ph = 0;
     EpiStatsAcc<BLOCK_N> stats_acc;
     stats_acc.init();
+    bool store_pending = false;
     for (int64_t t = tile0; t < p.total_tiles; t += tile_step) {
       const HlTile tc = hl_decode(p, t, CG, (int)rank);
       const int n0 = tc.nb * BLOCK_N;
       float* sb = sbias + acc * BLOCK_N;
-      for (int j = te; j < BLOCK_N; j += 128) {
+      for (int j = te; j < BLOCK_N; j += EPI_THREADS) {
         float v = p.bias ? p.bias[n0 + j] : 0.f;
         if (p.temb) v += p.temb[(int64_t)tc.n * p.temb_stride + p.temb_off + n0 + j];
         sb[j] = v;
@@ -437,7 +451,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
       }
       if constexpr (BLOCK_N == 16) {
         // conv_out form: the first cout_real accumulator columns go to an NCHW fp32 tensor
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         mbar_wait(&tfull[acc], acc_ph);
         tc_fence_after();
         const uint32_t taddr16 = tmem_base + (uint32_t)(acc * MT * BLOCK_N) + ((uint32_t)(q * 32) << 16);
@@ -464,12 +478,23 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         acc ^= 1; if (acc == 0) acc_ph ^= 1;
         continue;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * MT * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      if constexpr (BLOCK_N >= 32)
+      if constexpr (FUSE == 2) {
+        // warps 2-5 take accumulator 0, warps 6-9 accumulator 1 (same TMEM lane quadrants): half the epilogue latency
+        static_assert(MT == 2, "one epilogue warp group per stacked accumulator");
+        const int mh = (warp - 2) >> 2;
+        const bool valid1[1] = {valid[mh]};
+        const int64_t off1[1] = {off[mh]};
+        const int hrow1[1] = {tc.h0 + mh * half_rows + ((q * 32) >> p.tw_shift)};
+        epi_tile_tma<BLOCK_N, 1>(taddr + (uint32_t)(mh * BLOCK_N), sb, valid1, off1, p.res,
+                                 p.stats ? sstat + (mh * 4 + q) * BLOCK_N : nullptr, lane,
+                                 stage + (mh * 4 + q) * 4096, &maps.o, n0, tc.w0, hrow1, tc.n, store_pending);
+      } else if constexpr (BLOCK_N >= 32) {
         epi_tile<BLOCK_N, MT>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -477,12 +502,13 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
         else mbar_arrive(&tempty[acc]);
       }
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        stats_acc.add_tile(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        stats_acc.template add_tile<EW>(sstat, te, p.stats + ((int64_t)tc.n * p.cout + n0) * 2);
       }
       acc ^= 1; if (acc == 0) acc_ph ^= 1;
     }
     stats_acc.emit(te);
+    if (store_pending && lane == 0) bulk_wait_group0();   // the last tensor stores have left shared memory and landed
   }
 
   tc_fence_before();
@@ -496,9 +522,19 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
 }
 
 // ------------------------------------------------------------------ host side
+// DSG_TMA_OUT=0 keeps the direct-store epilogue (A/B switch)
+static bool tma_out_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DSG_TMA_OUT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, int MT, int CG, int FUSE>
 static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
-  using Cfg = HlCfg<BLOCK_N, MT, CG>;
+  using Cfg = HlCfg<BLOCK_N, MT, CG, FUSE == 2>;
   HlPlan p;
   memset(&p, 0, sizeof(p));
   const int oh = a->h, ow = a->w;  // GEMM pixel grid (per phase for mode 2)
@@ -507,13 +543,13 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   const int th = MT * (128 / tw);
   const int halo = a->mode == 0 ? 2 : 1;
   if (oh < th + halo) return DSG_HALO_SKIP;  // keep every TMA box inside the tensor extents
-  if (FUSE != 0 && a->mode != 0) return DSG_HALO_SKIP;
+  if (FUSE != 0 && a->mode != 0) return DSG_HALO_SKIP;   // fused GroupNorm / TMA-store forms: plain 3x3 only
   p.N = a->n; p.OH = oh; p.OW = ow; p.TW = tw; p.tw_shift = sh; p.TH = th;
   p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th * CG);  // a CTA pair stacks its two tiles vertically
   p.cout = a->cout; p.n_blocks = a->cout / BLOCK_N;
   const int cin_chunks = a->cin / 64;
   // the 3x3 input is one tensor, or (fused GroupNorm form) the channel concatenation of two raw tensors
-  const int cin1 = (FUSE != 0 && a->x2) ? a->cin1 : a->cin;
+  const int cin1 = (FUSE == 1 && a->x2) ? a->cin1 : a->cin;
   const int nsrc = cin1 < a->cin ? 2 : 1;
   const int src_chunks[2] = {cin1 / 64, (a->cin - cin1) / 64};
   const int src_map[2] = {0, 3};
@@ -533,7 +569,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
         HlGroup& G = p.grp[p.ngroups++];
         G.map = src_map[s]; G.dx = dx; G.dy0 = -1; G.nchunks = src_chunks[s]; G.ntaps = 3;
         G.chunk_off = s == 0 ? 0 : src_chunks[0];
-        G.transform = FUSE;
+        G.transform = FUSE == 1;
         for (int dy = -1; dy <= 1; ++dy) {
           G.row_off[dy + 1] = dy + 1;
           G.kb_base[dy + 1] = ((dy + 1) * 3 + (dx + 1)) * cin_chunks;
@@ -581,12 +617,18 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.stats = (long long*)a->out_stats;
   p.coef = (const float2*)a->gn_coef; p.cin_main = a->cin; p.IH = a->h; p.IW = a->w;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
+  if constexpr (FUSE == 2) {
+    static_assert(Cfg::STAGE, "no staging buffers in this configuration");
+    rc = make_map_a(&maps.o, dense_src(a->out, a->cout, oh, ow), a->n, tw, 32 / tw);
+    if (rc) return rc;
+    p.tma_out = 1;
+  }
   static SmemAttrCache attr;
   {
     cudaError_t e = ensure_dyn_smem(attr, igemm_halo_kernel<BLOCK_N, MT, CG, FUSE>, (size_t)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("igemm_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return DSG_ERR_CUDA; }
   }
-  const int threads = FUSE ? HL_THREADS_FUSED : HL_THREADS;
+  const int threads = FUSE == 1 ? HL_THREADS_FUSED : (FUSE == 2 ? HL_THREADS_TMA : HL_THREADS);
   const int64_t slots = num_sms() / CG;  // CTAs, or CTA pairs
   const int64_t grid = (p.total_tiles < slots ? p.total_tiles : slots) * CG;
   if constexpr (CG == 2) {
@@ -632,7 +674,13 @@ int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStre
   }
   if (cta_pair) {
     switch (block_n) {
-      case 64: return launch_halo<64, 2, 2, 0>(a, st);
+      case 64:
+        // FUSE = 2: fp16 NHWC output staged in shared memory and written by TMA tensor stores (plain 3x3 convs)
+        // — the layers whose main loop is short enough (3x3 over 64 channels, + at most a 64-channel shortcut panel) for
+        // the epilogue to pace the kernel; with more K the deeper weight ring of the plain form wins (measured)
+        if (a->mode == 0 && a->out && !a->out_nchw_f32 && a->cin == 64 && a->csc1 + a->csc2 <= 64 && tma_out_enabled())
+          return launch_halo<64, 2, 2, 2>(a, st);
+        return launch_halo<64, 2, 2, 0>(a, st);
       case 128: return launch_halo<128, 2, 2, 0>(a, st);
       case 256: return launch_halo<256, 1, 2, 0>(a, st);
       default: return DSG_HALO_SKIP;

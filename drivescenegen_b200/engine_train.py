@@ -218,7 +218,10 @@ class TrainProgram(_Program):
             self._colsum_job(colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr,
                              _p(total), None)
         nbytes = b * npx * c * 2
-        self._bemit("gn_bwd", {"bytes": 5 * nbytes + (nbytes if addend is not None else 0), "bytes_alg": 3 * nbytes},
+        # executed: pass 1 reads x, dy (+ writes g over dy when there is an activation); pass 2 reads x, g (+ the
+        # shortcut addend) and writes dx.  Algorithmic: read x, read dy, write dx.
+        self._bemit("gn_bwd", {"bytes": (5 + (1 if act else 0) + (1 if addend is not None else 0)) * nbytes,
+                               "bytes_alg": 3 * nbytes},
                     lambda st: check(lib.dsg_gn_bwd(*a1, st), "gn_bwd"))
 
     # ------------------------------------------------------------------ the backward program

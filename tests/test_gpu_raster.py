@@ -133,6 +133,18 @@ def test_agent_threshold_vs_oracle(n, h, w):
     assert np.array_equal(got, agent_threshold(allv[0, 2].numpy()))
 
 
+def lib_err(call):
+    """the keyword a failing C-ABI call leaves in dsg_last_error()."""
+    from drivescenegen_b200 import _lib
+    lib = _lib.load()
+    assert call(lib) != 0
+    msg = lib.dsg_last_error()
+    for key in (b"null pointer", b"mode", b"bad shape"):
+        if key in msg:
+            return key
+    return msg
+
+
 def test_raster_edge_cases_and_errors():
     from drivescenegen_b200 import _lib
     from drivescenegen_b200.hostapi import raster
@@ -147,7 +159,12 @@ def test_raster_edge_cases_and_errors():
     with pytest.raises(ValueError):
         raster.gray_masks(torch.zeros((1, 8, 8, 2), dtype=torch.uint8, device=dev))
     with pytest.raises(ValueError):
-        raster.image_to_sample(torch.zeros((1, 8, 8, 3), dtype=torch.float32, device=dev))
+        raster.image_to_sample(torch.zeros((1, 8, 8, 3), dtype=torch.float64, device=dev))
+    # float32 rasters are the .pkl branch (already in [0, 1]): Normalize only
+    f = torch.rand((1, 8, 8, 3), device=dev)
+    assert torch.equal(raster.image_to_sample(f), f.permute(0, 3, 1, 2).sub(0.5).div(0.5))
+    assert lib_err(lambda l: l.dsg_resize_to_sample(None, 0, None, 1, 8, 8, 3, 3, 4, 4, 0, None)) == b"null pointer"
+    assert lib_err(lambda l: l.dsg_resize_to_sample(None, 0, None, 1, 8, 8, 3, 3, 4, 4, 2, None)) == b"mode"
     with pytest.raises(ValueError):
         raster.agent_threshold(torch.zeros((3, 8, 8), dtype=torch.float64, device=dev))
     with pytest.raises(ValueError):

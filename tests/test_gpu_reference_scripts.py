@@ -114,8 +114,11 @@ def test_train_py_then_generation_py_run_unmodified_on_b200(tmp_path, monkeypatc
     assert sum(p.numel() for p in model.parameters()) == 56_574_595
     steps = len(g["train_dataloader"]) * cfg.num_epochs
     assert steps == 20
-    # >= 47 tensor-core 3x3 convs forward + their data gradients in every training step, all issued from train_loop
-    assert counts["train_loop"] >= steps * 47 * 2, counts
+    # >= 47 tensor-core 3x3 convs in every training forward, issued under train_loop's `model(noisy_pattern, ...)` frame;
+    # their data-gradient convs run from `accelerator.backward(loss)` on torch's autograd worker thread (no reference
+    # frame on that Python stack): counted as "other"
+    assert counts["train_loop"] >= steps * 47, counts
+    assert counts["other"] >= steps * 47, counts
     # evaluate(): 750 sampling steps per epoch = replays of a step graph captured (once per epoch's pipeline) from here
     assert counts["evaluate"] >= cfg.num_epochs * 47, counts
     assert launched > steps * 400, launched
