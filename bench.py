@@ -262,6 +262,8 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
         tt = torch.tensor([ms, e2e_s * 1000.0, ar_ms or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_s, ar_ms = tt[0].item(), tt[1].item() / 1000.0, tt[2].item()
+    flat_p = getattr(model, "_flat_params", None)
+    checksum = float(flat_p.double().sum().item()) if flat_p is not None else None   # same on every rank after N steps
     if rank != 0:
         return None
     pk = peaks()
@@ -338,8 +340,13 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
             "clocks": clocks,
             "e2e": {"value": world * B * K / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K},
-            "allreduce": None if world == 1 else {"bytes": 4 * sum(p.numel() for p in model.parameters()),
-                                                  "ms_alone": ar_ms, "collectives_per_step": 1},
+            "allreduce": None if world == 1 else {
+                "bytes": 4 * sum(p.numel() for p in model.parameters()), "ms_alone": ar_ms,
+                "overlap": os.environ.get("DSG_AR_OVERLAP", "1") != "0",
+                "how": "one flat fp32 gradient buffer, averaged in place by NCCL; its tail (up / mid / output layers, "
+                       "64 % of the bytes) is issued from inside the backward pass and runs under the down path's "
+                       "backward, the head follows when the backward returns"},
+            "param_checksum": checksum,
             "gpu_launches": K * per_step_launches, "roofline": roofline, "kernels": kernels, "breakdown": breakdown,
             "whole_step": {"flops": step_flops, "ms": ms / K,
                            "frac": step_flops / (ms / K * 1e-3) / 1e12 / pk["tflops_sustained"]},

@@ -9,10 +9,10 @@
 //   m1_g     = sum_{c in g} gamma_c A_c / count                  m2_g = sum_{c in g} gamma_c B_c / count
 //   dx       = rstd_g * (gamma_c * g - m1_g - xh * m2_g)
 // Two streaming passes: gn_bwd_stats_kernel (reads da, x) writes per-(sample, pixel-chunk, channel) partials of A and B
-// in a fixed layout and — when there is an activation — stores g over da IN PLACE (da is scratch: the dgrad conv that
-// produced it is its only writer and this backward its only reader), so the SiLU derivative (one MUFU + the fp16x2
-// arithmetic around it) is evaluated once per element, not once per pass; gn_bwd_apply_kernel (reads g, x) sums the chunk
-// partials in a fixed order — deterministic, no atomics — and writes dx with three FMAs per element, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
+// in a fixed layout; gn_bwd_apply_kernel (reads da, x again) sums the chunk partials in a fixed order — deterministic,
+// no atomics — and writes dx.  Both evaluate g with the SAME fp16x2 instruction sequence (one MUFU op per PAIR of
+// elements, silu_grad_h2): the fp32 form made both passes issue-bound at ~0.55 of the HBM rate, and storing g after the
+// first pass instead (measured) costs a sixth pass over the tensor for nothing — the kernels are memory-bound now, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
 // content of the destination: a tensor with two consumers), split over the two concatenated sources.  It can also emit
 // per-CTA column sums of what it wrote (the time-embedding / conv1-bias gradient of a ResnetBlock).
 // Forward statistics come from the same int64 per-channel totals the forward used (groupnorm.cu).
@@ -27,7 +27,7 @@ constexpr int GB_MAX_C = 2048;
 constexpr int GB_MAX_CHUNKS = 64;
 
 struct GnBwdArgs {
-  __half* dy;         // [n][hw][C] incoming gradient (w.r.t. the activated, normalised tensor); act != 0: overwritten by g
+  const __half* dy;   // [n][hw][C] incoming gradient (w.r.t. the activated, normalised tensor)
   const __half* x1; int c1; const long long* st1;
   const __half* x2; int c2; const long long* st2;
   const float* gamma; const float* beta;
@@ -139,8 +139,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
         const int64_t pp = p + (int64_t)u * ppi;
         if (pp < p_end) {
           rx[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
-          // da is rewritten below by this same thread: plain (coherent) load, not the read-only path
-          rd[u] = *reinterpret_cast<const uint4*>(a.dy + (base_px + pp) * C + ch0);
+          rd[u] = ldg_nc_v4(a.dy + (base_px + pp) * C + ch0);
         }
       }
 #pragma unroll
@@ -157,15 +156,13 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
               const __half2 h2 = __floats2half2_rn(fmaf(fx.x, gah[2 * k], ybh[2 * k]),
                                                    fmaf(fx.y, gah[2 * k + 1], ybh[2 * k + 1]));
               g2 = __hmul2(g2, silu_grad_h2(h2));
-              hd[k] = g2;
             }
-            const float2 g = __half22float2(g2);   // the sums see exactly the g the second pass reads
+            const float2 g = __half22float2(g2);   // exactly the g the second pass recomputes (same instructions)
             sA[2 * k] += g.x;
             sA[2 * k + 1] += g.y;
             sB[2 * k] = fmaf(g.x, fx.x, sB[2 * k]);
             sB[2 * k + 1] = fmaf(g.y, fx.y, sB[2 * k + 1]);
           }
-          if (ACT) stg_v4(a.dy + (base_px + pp) * C + ch0, rd[u]);
         }
       }
     }
@@ -187,13 +184,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   }
 }
 
-// Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1); g is what pass 1
-// left in a.dy.
+// Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1).
 #ifndef GB_APPLY_CTAS
 #define GB_APPLY_CTAS 2
 #endif
 #ifndef GB_APPLY_ILP
-#define GB_APPLY_ILP 2
+#define GB_APPLY_ILP 3
 #endif
 __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
@@ -250,12 +246,14 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs_acc[j] = 0.f; os_acc[j] = 0.f; }
   if (active) {
-    float ga[8], pc[8], qc[8];
+    float ga[8], gah[8], ybh[8], pc[8], qc[8];   // y / 2 = x * gah + ybh
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = ch0 + j, g = ch / cpg;
       const float mu = s_mean[g], rs = s_rstd[g];
       ga[j] = a.gamma[ch] * rs;
+      gah[j] = 0.5f * ga[j];
+      ybh[j] = 0.5f * (a.beta[ch] - mu * ga[j]);
       pc[j] = -rs * rs * s_m2[g];
       qc[j] = rs * (mu * rs * s_m2[g] - s_m1[g]);
     }
@@ -277,7 +275,17 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
         const int64_t pp = p + (int64_t)u * ppi;
         if (pp < p_end) {
           float fx[8], fd[8], fa[8], fo[8], r[8];
-          unpack8(rx[u], fx); unpack8(rd[u], fd); unpack8(ra[u], fa); unpack8(ro[u], fo);
+          unpack8(rx[u], fx); unpack8(ra[u], fa); unpack8(ro[u], fo);
+          if (a.act) {   // g = dy * SiLU'(y): fp16x2, one MUFU per pair — bit-identical to what pass 1 summed
+            __half2* hd = reinterpret_cast<__half2*>(&rd[u]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const __half2 h2 = __floats2half2_rn(fmaf(fx[2 * k], gah[2 * k], ybh[2 * k]),
+                                                   fmaf(fx[2 * k + 1], gah[2 * k + 1], ybh[2 * k + 1]));
+              hd[k] = __hmul2(hd[k], silu_grad_h2(h2));
+            }
+          }
+          unpack8(rd[u], fd);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float d = fmaf(ga[j], fd[j], fmaf(pc[j], fx[j], qc[j]));
@@ -393,7 +401,7 @@ using namespace dsg;
 
 extern "C" {
 
-int dsg_gn_bwd(void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
+int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
                float* osum1, float* osum2, int32_t parts, int32_t n, int64_t hw, int32_t groups, void* stream) {
@@ -414,7 +422,7 @@ int dsg_gn_bwd(void* dy, const void* x1, int32_t c1, const void* stats1, const v
                 "dsg_gn_bwd: unaligned pointer");
   if (n == 0) return DSG_OK;
   GnBwdArgs a;
-  a.dy = (__half*)dy;
+  a.dy = (const __half*)dy;
   a.x1 = (const __half*)x1; a.c1 = c1; a.st1 = (const long long*)stats1;
   a.x2 = (const __half*)x2; a.c2 = c2; a.st2 = (const long long*)stats2;
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.act = act;

@@ -746,6 +746,7 @@ class _Program:
                 x, hw = out, nhw
                 skips.append((x, blk["ch"], hw))
         mid = eng.mid
+        self._record({"kind": "boundary"})   # backward: everything recorded after this point is done when it is reached
         out = self._new("m0", hw, mid["resnets"][0]["cout"])
         self._record(self._resnet(mid["resnets"][0], x, None, hw, out))
         x = out

@@ -39,6 +39,8 @@ class TrainProgram(_Program):
         self.bwd_info: List[Tuple[str, dict]] = []
         self._uid = 0
         self.dout_ptr = C.c_void_p(0)
+        self.slot = 0                 # which of the two flat gradient buffers this program writes (hostapi.training)
+        self.on_early_ready = None    # hook(program): the "early" slice of the flat gradient buffer is complete
         super().__init__(eng, batch, h, w)
         self._build_backward()
 
@@ -218,9 +220,9 @@ class TrainProgram(_Program):
             self._colsum_job(colsum.data_ptr(), b, parts, c, per_n.data_ptr(), stride, off, self.inv_scale_ptr,
                              _p(total), None)
         nbytes = b * npx * c * 2
-        # executed: pass 1 reads x, dy (+ writes g over dy when there is an activation); pass 2 reads x, g (+ the
-        # shortcut addend) and writes dx.  Algorithmic: read x, read dy, write dx.
-        self._bemit("gn_bwd", {"bytes": (5 + (1 if act else 0) + (1 if addend is not None else 0)) * nbytes,
+        # executed: pass 1 reads x, dy; pass 2 reads x, dy (+ the shortcut addend) and writes dx.  Algorithmic: read x,
+        # read dy, write dx.
+        self._bemit("gn_bwd", {"bytes": (5 + (1 if addend is not None else 0)) * nbytes,
                                "bytes_alg": 3 * nbytes},
                     lambda st: check(lib.dsg_gn_bwd(*a1, st), "gn_bwd"))
 
@@ -240,6 +242,7 @@ class TrainProgram(_Program):
         # end; their inputs therefore live in per-call scratch buffers instead of shared ones
         self._rjobs: List[dict] = []
         self._ruid = 0
+        self._rlaunch = 0
         for rec in reversed(self.records):
             getattr(self, "_bwd_" + rec["kind"])(rec)
         self._emit_reduce_jobs()
@@ -249,8 +252,17 @@ class TrainProgram(_Program):
         self._ruid += 1
         return f"{name}#{self._ruid}"
 
+    def _bwd_boundary(self, rec):
+        """Between the mid block and the down path: every gradient of the up / mid / output layers has been produced.
+        Their finalisers run now (instead of with everybody else's at the end) and the hook lets the data-parallel
+        all-reduce of that slice of the flat gradient buffer start under the rest of the backward pass."""
+        self._emit_reduce_jobs()
+        if not self._sizing:
+            self._bemit("early_grads_ready", {}, lambda st: self.on_early_ready(self) if self.on_early_ready else None)
+
     def _emit_reduce_jobs(self):
         if self._sizing or not self._rjobs:
+            self._rjobs = []
             return
         from ._lib import ReduceJob
         arr = (ReduceJob * len(self._rjobs))()
@@ -264,12 +276,14 @@ class TrainProgram(_Program):
             r.block_begin = blk
             blk += (j["c"] + 31) // 32
         raw = bytes(arr)
-        dev = self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/reduce_jobs", len(raw), torch.uint8)
+        self._rlaunch += 1
+        dev = self.eng.arena.get(f"train/{self.b}x{self.h}x{self.w}/reduce_jobs{self._rlaunch}", len(raw), torch.uint8)
         dev.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
         lib, njobs, total = self.lib, len(self._rjobs), blk
         ptr = dev.data_ptr()
         self._bemit("colsum_finalize", {"jobs": njobs},
                     lambda st: check(lib.dsg_reduce_rows_batched(ptr, njobs, total, st), "reduce_rows_batched"))
+        self._rjobs = []
 
     def _colsum_job(self, src: int, n: int, parts: int, c: int, per_n, stride, off, inv, total, total2):
         self._rjobs.append(dict(src=src, n=n, parts=parts, c=c, comps=1, sample_stride=parts * c, part_stride=c,

@@ -267,6 +267,7 @@ class Accelerator:
         self._flat_grad: Optional[torch.Tensor] = None
         self._fused_state = {}
         self._ctl = None
+        self._early = None
         self._scale_host: Optional[float] = None
         self._growth_tracker = 0
         self.trackers = []
@@ -355,7 +356,8 @@ class Accelerator:
     def _flatten_parameters(model: torch.nn.Module):
         """Re-home every parameter in ONE flat fp32 buffer (same Parameter objects, same values): the fused AdamW
         kernel and the single gradient all-reduce then work on whole buffers instead of 160 small tensors."""
-        params = list(model.parameters())
+        from .training import flat_layout
+        params = [p for _, p in flat_layout(model)[0]]   # the order of the flat GRADIENT buffers (hostapi.training)
         if not params or getattr(model, "_flat_params", None) is not None:
             return
         if any(p.dtype != torch.float32 for p in params):
@@ -363,12 +365,15 @@ class Accelerator:
         total = sum(p.numel() for p in params)
         flat = torch.empty(total, dtype=torch.float32, device=params[0].device)
         off = 0
+        offsets = {}
         for p in params:
             n = p.numel()
             flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = flat[off:off + n].view(p.shape)
+            offsets[id(p)] = off
             off += n
         model._flat_params = flat
+        model._flat_offsets = offsets
 
     def _flat_grad_of(self, model) -> Optional[torch.Tensor]:
         """the flat gradient buffer the engine's last backward wrote, if the parameters' .grad alias it."""
@@ -384,6 +389,11 @@ class Accelerator:
         if last.data_ptr() != flat.data_ptr() + 4 * (flat.numel() - last.numel()):
             return None
         return flat
+
+    @staticmethod
+    def _same_params(a, b) -> bool:
+        """the same set of Parameter objects (the flat buffers keep their own order, see hostapi.training.flat_layout)"""
+        return len(a) == len(b) and {id(p) for p in a} == {id(p) for p in b}
 
     def _loss_scale_value(self) -> float:
         if self.scaler is None:
@@ -413,7 +423,7 @@ class Accelerator:
                 or grp.get("differentiable"):
             return False
         fg = getattr(model, "_flat_grads", None)
-        if fg is None or len(grp["params"]) != len(fg.params) or any(a is not b for a, b in zip(grp["params"], fg.params)):
+        if fg is None or not self._same_params(grp["params"], fg.params):
             return False
         if fg.params[0].data_ptr() != flat_p.data_ptr():
             return False
@@ -468,16 +478,15 @@ class Accelerator:
         st = self._fused_state.get(id(opt))
         if st is None:
             return
-        off = 0
+        offsets = self._models[0]._flat_offsets
         for p in opt.param_groups[0]["params"]:
-            n = p.numel()
+            n, off = p.numel(), offsets[id(p)]
             s = opt.state[p]
             m = s.get("exp_avg")
             if m is None or m.data_ptr() != st["m"].data_ptr() + 4 * off:
                 s["exp_avg"] = st["m"][off:off + n].view_as(p)
                 s["exp_avg_sq"] = st["v"][off:off + n].view_as(p)
             s["step"] = torch.tensor(float(st["step"]))
-            off += n
 
     def _import_fused_state(self, opt):
         if len(opt.param_groups) != 1:
@@ -494,13 +503,12 @@ class Accelerator:
         if st is None:
             st = {"m": torch.zeros_like(flat_p), "v": torch.zeros_like(flat_p), "step": 0}
             self._fused_state[id(opt)] = st
-        off = 0
+        offsets = self._models[0]._flat_offsets
         for p in params:
-            n = p.numel()
+            n, off = p.numel(), offsets[id(p)]
             s = opt.state[p]
             st["m"][off:off + n].copy_(s["exp_avg"].reshape(-1))
             st["v"][off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
-            off += n
         st["step"] = int(float(opt.state[params[0]]["step"]))
         self._export_fused_state(opt)
 
@@ -523,14 +531,63 @@ class Accelerator:
         else:
             yield
 
+    def _reduce_mean(self, t: torch.Tensor, async_op: bool = False):
+        """in-place mean over ranks: NCCL averages inside the collective; gloo sums and the division is a second pass"""
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op), False
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op), True
+
+    def _arm_early_allreduce(self):
+        """Let the backward pass start the all-reduce of the gradients that are complete first (up / mid / output layers:
+        the tail of the flat buffer, hostapi.training.flat_layout) while the down path's backward is still computing.
+        NCCL runs it on the process group's own stream, ordered after the point of the backward where it was issued; the
+        rest of the buffer follows when the backward returns.  Same single flat buffer, same values: the collective is
+        only split in two so that most of it hides under compute."""
+        self._early = None
+        if not (self.use_distributed and self.sync_gradients and len(self._models) == 1) \
+                or os.environ.get("DSG_AR_OVERLAP", "1") == "0":
+            return
+        model = self._models[0]
+        fg = getattr(model, "_flat_grads", None)
+        eng = getattr(model, "_engine", None)
+        if fg is None or eng is None or any(p.grad is not None for p in fg.params):
+            return   # gradients are being accumulated into existing .grad tensors: the flat buffer is not the final word
+
+        def hook(prog):
+            flat = fg.flat[prog.slot]
+            work, needs_div = self._reduce_mean(flat[fg.early_offset:], async_op=True)
+            self._early = (flat.data_ptr(), work, needs_div)
+
+        for prog in eng.train_programs.values():
+            prog.on_early_ready = hook
+
+    def _disarm_early_allreduce(self):
+        model = self._models[0] if len(self._models) == 1 else None
+        eng = getattr(model, "_engine", None) if model is not None else None
+        if eng is not None:
+            for prog in eng.train_programs.values():
+                prog.on_early_ready = None
+
     def _allreduce_grads(self):
-        """ONE all-reduce over a single flat gradient buffer, averaged over ranks."""
+        """ONE flat gradient buffer, averaged over ranks; its tail may already be in flight."""
         if len(self._models) == 1:
             flat = self._flat_grad_of(self._models[0])
+            early = getattr(self, "_early", None)
+            self._early = None
             if flat is not None:   # the engine's backward already wrote one flat buffer: reduce it in place
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                flat.mul_(1.0 / self.num_processes)
+                if early is not None and early[0] == flat.data_ptr():
+                    off = self._models[0]._flat_grads.early_offset
+                    _, div = self._reduce_mean(flat[:off])
+                    early[1].wait()
+                    if div or early[2]:
+                        flat.mul_(1.0 / self.num_processes)
+                    return
+                _, div = self._reduce_mean(flat)
+                if div:
+                    flat.mul_(1.0 / self.num_processes)
                 return
+            if early is not None:
+                early[1].wait()   # (cannot happen: the hook only fires when .grad will alias the flat buffer)
         params = [p for m in self._models for p in m.parameters() if p.grad is not None]
         if not params:
             return
@@ -551,10 +608,15 @@ class Accelerator:
 
     def backward(self, loss: torch.Tensor, **kwargs):
         loss = loss / self.gradient_accumulation_steps
-        if self.scaler is not None:
-            self.scaler.scale(loss).backward(**kwargs)
-        else:
-            loss.backward(**kwargs)
+        self._arm_early_allreduce()
+        try:
+            if self.scaler is not None:
+                self.scaler.scale(loss).backward(**kwargs)
+            else:
+                loss.backward(**kwargs)
+        finally:
+            if self.use_distributed:
+                self._disarm_early_allreduce()
         if self.use_distributed and self.sync_gradients:
             self._allreduce_grads()
 
@@ -571,7 +633,7 @@ class Accelerator:
             # kernel (the .grad tensors keep their scaled values)
             plist = list(parameters)
             fg = getattr(self._models[0], "_flat_grads", None)
-            if fg is not None and len(plist) == len(fg.params) and all(a is b for a, b in zip(plist, fg.params)):
+            if fg is not None and self._same_params(plist, fg.params):
                 ctl = self._fused_grad_norm(self._models[0], max_norm)
                 if ctl is not None:
                     return ctl[0]

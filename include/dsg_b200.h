@@ -267,8 +267,7 @@ int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
                         void* stream);
 
 /* GroupNorm(+SiLU) backward over cat(x1, x2) (see dsg_gn_apply for the forward and the statistics format).
- *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT — SCRATCH: with act != 0 the call overwrites it with
- *   g = dy * SiLU'(GroupNorm(x)) (the first pass stores it so the second does not recompute it).  partial: float[n][chunks + 1][c1+c2][2] scratch
+ *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: float[n][chunks + 1][c1+c2][2] scratch
  *   (chunk partials, then one slot per sample holding the sums behind d beta / d gamma, read by dsg_gn_bwd_params),
  *   1 <= chunks <= 64.
  *   addend (may be NULL): h16 [n][hw][c1+c2] added to the input gradient (the ResnetBlock shortcut's gradient).
@@ -279,7 +278,7 @@ int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
  *            conv1-bias gradient of a ResnetBlock;
  *     osum1 float[n][parts][c1], osum2 float[n][parts][c2]: of the FINAL values stored to dx1 / dx2 — when this call is
  *            the last writer of that gradient tensor, its producer's bias gradient without another read. */
-int dsg_gn_bwd(void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
+int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, const void* x2, int32_t c2,
                const void* stats2, const float* gamma, const float* beta, float eps, int32_t act, float* partial,
                int32_t chunks, const void* addend, void* dx1, int32_t acc1, void* dx2, int32_t acc2, float* colsum,
                float* osum1, float* osum2, int32_t parts, int32_t n, int64_t hw, int32_t groups, void* stream);

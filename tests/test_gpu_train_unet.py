@@ -217,3 +217,108 @@ def test_full_size_training_step_properties_batch32_256():
     assert abs(0.5 * (la + lb) - l1) <= 1e-5 * abs(l1)
     # each half runs with its own power-of-two gradient scale and fp16 roundings: agreement at fp16 resolution
     assert _rel(0.5 * (ga + gb), full1) < 5e-3
+
+
+def test_early_gradient_slice_is_complete_at_the_backward_boundary():
+    """Data-parallel overlap: the flat gradient buffer is laid out [late ..., early ...] and the backward
+    program fires a hook once it has crossed from the mid block into the down path.  At that moment every gradient of the
+    early slice (up blocks, mid block, conv_norm_out, conv_out, minus the time_emb_proj layers) must already hold its
+    FINAL value — that is what lets the all-reduce of that slice run under the rest of the backward pass."""
+    import torch.nn.functional as F
+    from drivescenegen_b200.hostapi.training import flat_layout
+    _, model = _pair(CFG_REF)
+    model.train()
+    order, early_off = flat_layout(model)
+    names = [n for n, _ in order]
+    first_early = sum(1 for n, p in order if sum(q.numel() for _, q in order[:names.index(n)]) < early_off)
+    assert all(n.startswith(("up_blocks.", "mid_block.", "conv_norm_out.", "conv_out.")) and "time_emb_proj" not in n
+               for n in names[first_early:])
+    assert all("time_emb_proj" in n or n.startswith(("conv_in.", "time_embedding.", "down_blocks."))
+               for n in names[:first_early])
+    total = sum(p.numel() for _, p in order)
+    assert 0.5 < (total - early_off) / total < 0.8          # most of the buffer can hide under the down path
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 64, 64, generator=g).to(_dev())
+    target = torch.randn(2, 3, 64, 64, generator=g).to(_dev())
+    t = torch.tensor([7, 911], device=_dev())
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        F.mse_loss(model(x, t, return_dict=False)[0], target).backward()
+    run()                                                  # builds the program
+    fg = model._flat_grads
+    seen = {}
+
+    def hook(prog):
+        seen["early"] = fg.flat[prog.slot][fg.early_offset:].clone()      # stream-ordered snapshot at the boundary
+        seen["late"] = fg.flat[prog.slot][:fg.early_offset].clone()
+    for prog in model._engine.train_programs.values():
+        prog.on_early_ready = hook
+    fg.flat[0].fill_(float("nan"))                         # nothing may survive from the first pass
+    fg.flat[1].fill_(float("nan"))
+    run()
+    torch.cuda.synchronize()
+    final = fg.flat[fg.last]
+    assert "early" in seen, "the backward program never reached its boundary op"
+    assert torch.isfinite(final).all()
+    assert torch.equal(seen["early"], final[fg.early_offset:])
+    assert not torch.equal(seen["late"].nan_to_num(0.0), final[:fg.early_offset])   # the late slice was still being written
+    # .grad tensors are views of the flat buffer in layout order
+    off = 0
+    for n, p in order:
+        assert p.grad.data_ptr() == final.data_ptr() + 4 * off, n
+        off += p.numel()
+
+
+def test_fused_adamw_state_is_visible_in_state_dict_and_resumes_bit_exactly():
+    """the fused AdamW path keeps its moments in flat buffers; optimizer.state / state_dict() must expose them
+    (checkpoint) and load_state_dict() must restore them (resume): an interrupted-and-resumed run equals an
+    uninterrupted one bit for bit."""
+    from drivescenegen_b200.hostapi import Accelerator, DDPMScheduler, get_cosine_schedule_with_warmup
+    g = torch.Generator().manual_seed(22)
+    batches = [torch.rand(2, 3, 64, 64, generator=g).mul(2).sub(1).to(_dev()) for _ in range(4)]
+
+    def fresh():
+        _, model = _pair(CFG_C1, seed=4)
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        lrs = get_cosine_schedule_with_warmup(optimizer=opt, num_warmup_steps=1, num_training_steps=8)
+        return model, opt, lrs, Accelerator(mixed_precision="no")
+
+    model, opt, lrs, acc = fresh()
+    _train_loop(model, acc, opt, lrs, DDPMScheduler(), batches, True)
+    want = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+
+    model, opt, lrs, acc = fresh()
+    _train_loop(model, acc, opt, lrs, DDPMScheduler(), batches[:2], True)
+    wrapped = acc._optimizers[0]
+    sd = wrapped.state_dict()
+    assert len(sd["state"]) == len(list(model.parameters()))
+    st0 = sd["state"][0]
+    assert float(st0["step"]) == 2.0 and st0["exp_avg"].abs().sum().item() > 0 and st0["exp_avg_sq"].min().item() >= 0
+    p0 = next(iter(model.parameters()))
+    assert wrapped.state[p0]["exp_avg"].shape == p0.shape
+    ckpt = {"model": {k: v.clone() for k, v in model.state_dict().items()},
+            "opt": {"state": {k: {kk: vv.clone() for kk, vv in v.items()} for k, v in sd["state"].items()},
+                    "param_groups": sd["param_groups"]},
+            "lrs": lrs.state_dict()}
+
+    model2, opt2, lrs2, acc2 = fresh()
+    model2.load_state_dict(ckpt["model"])
+    model2, opt2w, lrs2w = acc2.prepare(model2, opt2, lrs2)
+    opt2w.load_state_dict(ckpt["opt"])
+    lrs2w.load_state_dict(ckpt["lrs"])
+    sched = DDPMScheduler()
+    import torch.nn.functional as F
+    for i, clean in enumerate(batches[2:], start=2):
+        noise = torch.randn(clean.shape, generator=torch.Generator().manual_seed(i)).to(clean.device)
+        ts = torch.randint(0, 1000, (clean.shape[0],), generator=torch.Generator().manual_seed(99)).long().to(clean.device)
+        with acc2.accumulate(model2):
+            loss = F.mse_loss(model2(sched.add_noise(clean, noise, ts), ts, return_dict=False)[0], noise)
+            acc2.backward(loss)
+            acc2.clip_grad_norm_(model2.parameters(), 1.0)
+            opt2w.step()
+            lrs2w.step()
+            opt2w.zero_grad()
+    got = torch.cat([p.detach().reshape(-1) for p in model2.parameters()])
+    assert torch.equal(got, want)

@@ -11,6 +11,7 @@
 #   launches-train       same for one training step
 #   full <regex> <name>  ncu --set full of the kernels matching <regex> in the sampling step -> <name>.ncu-rep + raw csv
 #   full-train <regex> <name>   same inside the training step
+#                        (NCU_EXTRA="-c 12" in the environment limits the number of profiled launches)
 #   sweep                tools/op_sweep.py --raster
 # Stages are separated by `--`:  bash tools/gpu.sh r2a test -- bench --steps 40 -- launches
 TAG=$1; shift
@@ -38,7 +39,7 @@ run_stage() {
     full|full-train)
       local script=tools/profile_step.py; [ $s = full-train ] && script=tools/profile_train_step.py
       local rx=$1 name=$2; shift 2
-      timeout 900 ncu $NCU_F -k regex:"$rx" -o $O/$name python $script "$@" > $O/ncu_$name.log 2>&1
+      timeout 1500 ncu $NCU_F $NCU_EXTRA -k regex:"$rx" -o $O/$name python $script "$@" > $O/ncu_$name.log 2>&1
       ncu -i $O/$name.ncu-rep --page raw --csv > $O/${name}_raw.csv 2>/dev/null
       python tools/ncu_raw_summary.py $O/${name}_raw.csv > $O/${name}_summary.txt 2>&1 ;;
     sweep) timeout 600 python tools/op_sweep.py --raster --out $O/op_sweep.json > $O/op_sweep.log 2>&1 ;;
