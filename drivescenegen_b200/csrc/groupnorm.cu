@@ -20,7 +20,14 @@ namespace dsg {
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_GROUPS = 64;
 constexpr int GN_MAX_C = 2048;  // 256 threads x 8 channels
-constexpr int GN_ILP = 4;
+#ifndef GN_ILP_DEF
+#define GN_ILP_DEF 4
+#endif
+constexpr int GN_ILP = GN_ILP_DEF;
+#ifndef GN_CTAS_DEF
+#define GN_CTAS_DEF 3
+#endif
+constexpr int GN_CTAS = GN_CTAS_DEF;   // resident gn_apply CTAs per SM (register-limited)
 
 // ------------------------------------------------------------------ per-channel statistics of one tensor
 // grid (chunks, n); thread = (pixel row, 8-channel vector).  Block partials in fp32 (<= ~1024 pixels), totals in int64.
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const __half* __re
 }
 
 // ------------------------------------------------------------------ normalise + affine + activation
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const __half* __restrict__ x1, int c1,
+__global__ void __launch_bounds__(GN_THREADS, GN_CTAS) gn_apply_kernel(const __half* __restrict__ x1, int c1,
                                                               const long long* __restrict__ st1,
                                                               const __half* __restrict__ x2, int c2,
                                                               const long long* __restrict__ st2,
@@ -288,7 +295,7 @@ int dsg_gn_apply(const void* x1, int32_t c1, const void* stats1, const void* x2,
   // about one full wave of CTAs (3 per SM at 74 registers) for big tensors — the per-CTA prologue is amortised and there is no
   // tail wave — but never less than one batch of loads per thread
   const int64_t batch_px = (int64_t)ppi * GN_ILP;
-  int64_t per_sample = (148 * 3) / n;
+  int64_t per_sample = (num_sms() * GN_CTAS) / n;
   if (per_sample < 1) per_sample = 1;
   int64_t px_per_cta = ceil_div64(ceil_div64(hw, per_sample), batch_px) * batch_px;
   int64_t ctas = ceil_div64(hw, px_per_cta);

@@ -42,6 +42,7 @@ struct IgPlan {
   int temb_stride, temb_off;
   long long* stats;   // optional per-channel GroupNorm totals of the output: int64 [N][cout][2] (groupnorm.cu)
   int a_bytes;        // bytes one A box delivers (TH clipped to the image height)
+  int xpose;           // transposed epilogue stores through shared memory (epi_tile)
   int64_t total_tiles;
 };
 struct alignas(64) IgMaps {
@@ -55,8 +56,9 @@ struct IgCfg {
   static constexpr int STAGE_BYTES = IG_A_BYTES + B_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 256 -> 4, 128 -> 6, 64 -> 8
   static constexpr int TMEM_COLS = 2 * BLOCK_N;              // double-buffered fp32 accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + 4 * BLOCK_N * 4 /*GN stats*/ +
-                                    256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int EPI_STAGE = 4 * EPI_STAGE_BYTES_PER_WARP;   // transposed epilogue stores (igemm_common.cuh)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE + 2 * BLOCK_N * 4 /*bias*/ +
+                                    4 * BLOCK_N * 4 /*GN stats*/ + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 struct TileCoord {
@@ -82,7 +84,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  float* sbias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;                       // [4 warps][2 KB]
+  float* sbias = reinterpret_cast<float*>(epi_stage + Cfg::EPI_STAGE);         // [2][BLOCK_N]
   float* sstat = sbias + 2 * BLOCK_N;                                          // [4][BLOCK_N / 2][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sstat + 4 * BLOCK_N);
   uint64_t* full_bar = bars;                 // [STAGES]
@@ -190,7 +193,8 @@ igemm_kernel(const __grid_constant__ IgMaps maps, const __grid_constant__ IgPlan
       const int64_t off[1] = {(int64_t)tc.n * p.oN + (int64_t)(h * p.omul + tc.pa) * p.oH +
                               (int64_t)(w * p.omul + tc.pb) * p.oW + n0};
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(q * 32) << 16);
-      epi_tile<BLOCK_N, 1>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
+      epi_tile<BLOCK_N, 1>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane,
+                           p.xpose ? epi_stage + q * EPI_STAGE_BYTES_PER_WARP : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -450,6 +454,7 @@ static int launch_igemm(const IgPlan& plan_in, cudaStream_t st) {
   IgPlan p = plan_in;
   p.n_blocks = p.cout / BLOCK_N;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
+  p.xpose = epi_xpose_enabled() ? 1 : 0;
   IgMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int box_h = p.a_bytes / (128 * p.TW);
@@ -569,6 +574,9 @@ int dsg_conv(const dsg_conv_args* a, void* stream) {
   }
   int bn = a->block_n;
   if (bn == 0) bn = (a->cout % 256 == 0) ? 256 : (a->cout % 128 == 0 ? 128 : 64);
+  // 1x1 convs over few channels are all epilogue: N = 64 tiles get the eight-warp TMA-store form of the halo kernel
+  // (the activation tile is re-read from L2 once per 64 output channels, which is cheap at cin <= 128)
+  if (a->block_n == 0 && a->mode == 3 && a->cin <= 128 && a->cout % 64 == 0) bn = 64;
   DSG_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && a->cout % bn == 0, "dsg_conv: bad block_n %d for cout %d", bn,
                 a->cout);
   if (a->impl != 2) {

@@ -44,11 +44,39 @@ __device__ __forceinline__ void warp_pairsum16x2(float* a, float* b, int lane) {
 // One CTA tile of the epilogue for one warp (32 rows): MT stacked accumulators of BLOCK_N fp32 columns each at
 // taddr (+ m * BLOCK_N), slice by slice (c outer, m inner).  The tcgen05.ld of the next slice is in flight while
 // the current one is converted; the residual (if any) is register-prefetched two slices ahead.
+// Stores: with one pixel per lane a direct STG.128 touches 32 different lines with 16 bytes each — every 32-byte sector
+// is written in two halves by two instructions and the LSU processes 32 wavefronts per instruction.  With a staging
+// buffer (stage_warp: 2 KB per epilogue warp, nullptr = direct stores) the warp parks its 32 pixels x 64 bytes in shared
+// memory (16-byte chunks XOR-swizzled: conflict-free both ways) and reads them back TRANSPOSED: lane L then stores chunk
+// (L & 3) of pixel (8 i + L / 4), i = 0..3, so one instruction writes eight whole 64-byte segments (full sectors), for
+// any pixel stride / sub-pixel phase.  The pixels' offsets come from their owner lanes by shuffle, once per tile.
+constexpr int EPI_STAGE_BYTES_PER_WARP = 2048;
+// DSG_EPI_XPOSE=0 keeps the direct stores (A/B switch)
+inline bool epi_xpose_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DSG_EPI_XPOSE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, int MT>
 __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const bool (&valid)[MT],
                                          const int64_t (&off)[MT], __half* out, const __half* res,
-                                         float* sstat_warp /* [BLOCK_N / 2][2] or nullptr */, int lane) {
+                                         float* sstat_warp /* [BLOCK_N / 2][2] or nullptr */, int lane,
+                                         uint8_t* stage_warp = nullptr) {
   constexpr int NCH = BLOCK_N / 32, NIT = NCH * MT;
+  int64_t offT[MT][4];
+  uint32_t vmask[MT];
+  if (stage_warp) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      vmask[m] = __ballot_sync(0xffffffffu, valid[m]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) offT[m][i] = __shfl_sync(0xffffffffu, off[m], i * 8 + (lane >> 2));
+    }
+  }
   uint32_t v[2][32];
   // residual: register-prefetched TWO slices ahead (one ahead left a full L2 / DRAM round trip on every slice)
   uint4 rn[2][4];
@@ -121,7 +149,20 @@ __device__ __forceinline__ void epi_tile(uint32_t taddr, const float* sb, const 
         if (!(lane & 1)) reinterpret_cast<float2*>(sstat_warp)[c * 16 + (lane >> 1)] = make_float2(a1[0], a2[0]);
       }
     }
-    if (valid[m]) {
+    if (stage_warp) {
+      uint8_t* mine = stage_warp + lane * 64;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine + ((j ^ sw) << 4)) = pack8(f + j * 8);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int px = i * 8 + (lane >> 2);
+        const uint4 pk = *reinterpret_cast<const uint4*>(stage_warp + px * 64 + (((lane & 3) ^ ((px >> 1) & 3)) << 4));
+        if ((vmask[m] >> px) & 1u) stg_v4(out + offT[m][i] + c * 32 + (lane & 3) * 8, pk);
+      }
+      __syncwarp();   // the next slice overwrites the staging buffer
+    } else if (valid[m]) {
       __half* op = out + off[m] + c * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) stg_v4(op + j, pack8(f + j));

@@ -58,6 +58,7 @@ struct HlPlan {
   const float2* coef;  // fused GroupNorm + SiLU of the input: [N][cin_main] (a / 2, b / 2); act = h + h tanh(h), h = a x / 2 + b / 2
   int cin_main;        // channels of the (concatenated) 3x3 input
   int IH, IW;          // extents of the 3x3 input (masking of the zero padding under the fused transform)
+  int xpose;           // transposed epilogue stores through shared memory (epi_tile)
   int tma_out;         // the fp16 NHWC output goes through the staging buffers + TMA stores (maps.o)
   int64_t total_tiles;
 };
@@ -86,8 +87,12 @@ struct HlCfg {
   static constexpr bool STAGE = STG;
   static_assert(!STG || (BLOCK_N == 64 && CG == 2), "staging buffers are sized for the BLOCK_N = 64 CTA-pair form");
   static constexpr int STAGE_BYTES = STAGE ? 4 * MT * 4096 : 0;
+  // transposed epilogue stores (epi_tile, igemm_common.cuh) wherever 8 KB are left: not the N = 256 forms (their rings
+  // fill shared memory; the epilogue hides under a long main loop there) and not the single-CTA N = 128 form
+  static constexpr bool XPOSE = !STG && BLOCK_N >= 32 && BLOCK_N != 256 && !(BLOCK_N == 128 && CG == 1);
+  static constexpr int XPOSE_BYTES = XPOSE ? 4 * EPI_STAGE_BYTES_PER_WARP : 0;
   static constexpr int SMEM_BYTES =
-      RING_BYTES + STAGE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + (STG ? 8 : 4) * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
+      RING_BYTES + STAGE_BYTES + XPOSE_BYTES + 2 * BLOCK_N * 4 /*bias*/ + (STG ? 8 : 4) * BLOCK_N * 4 /*GN stats*/ + 512 /*barriers*/ + 1024 /*align*/;
   static_assert(3 * NA + 2 * NB + 4 <= 60, "barrier area overflow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem overflow");
@@ -197,7 +202,7 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + NA * Cfg::A_SLOT;
   uint8_t* stage = smem + Cfg::RING_BYTES;                          // [4 warps][MT][4 KB], 1024-byte aligned
-  float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::STAGE_BYTES);  // [2][BLOCK_N]
+  float* sbias = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::STAGE_BYTES + Cfg::XPOSE_BYTES);  // [2][BLOCK_N]
   constexpr int EW = FUSE == 2 ? 8 : 4;                             // epilogue warps
   constexpr int EPI_THREADS = EW * 32;
   float* sstat = sbias + 2 * BLOCK_N;                               // [EW][BLOCK_N / 2][2]
@@ -493,7 +498,8 @@ igemm_halo_kernel(const __grid_constant__ HlMaps maps, const __grid_constant__ H
                                  p.stats ? sstat + (mh * 4 + q) * BLOCK_N : nullptr, lane,
                                  stage + (mh * 4 + q) * 4096, &maps.o, n0, tc.w0, hrow1, tc.n, store_pending);
       } else if constexpr (BLOCK_N >= 32) {
-        epi_tile<BLOCK_N, MT>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane);
+        epi_tile<BLOCK_N, MT>(taddr, sb, valid, off, p.out, p.res, p.stats ? sstat + q * BLOCK_N : nullptr, lane,
+                              (Cfg::XPOSE && p.xpose) ? stage + q * EPI_STAGE_BYTES_PER_WARP : nullptr);
       }
       tc_fence_before();
       __syncwarp();
@@ -532,6 +538,16 @@ static bool tma_out_enabled() {
   return v == 1;
 }
 
+// DSG_HALO_1X1=0 sends 1x1 convs back to the tap-streaming kernel (A/B switch)
+static bool halo_1x1_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DSG_HALO_1X1");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, int MT, int CG, int FUSE>
 static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   using Cfg = HlCfg<BLOCK_N, MT, CG, FUSE == 2>;
@@ -541,9 +557,10 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   int tw, sh;
   if (ow >= 16) { tw = 16; sh = 4; } else if (ow >= 8) { tw = 8; sh = 3; } else return DSG_HALO_SKIP;
   const int th = MT * (128 / tw);
-  const int halo = a->mode == 0 ? 2 : 1;
+  const int halo = a->mode == 0 ? 2 : (a->mode == 3 ? 0 : 1);
   if (oh < th + halo) return DSG_HALO_SKIP;  // keep every TMA box inside the tensor extents
-  if (FUSE != 0 && a->mode != 0) return DSG_HALO_SKIP;   // fused GroupNorm / TMA-store forms: plain 3x3 only
+  if (FUSE == 1 && a->mode != 0) return DSG_HALO_SKIP;                  // fused GroupNorm: plain 3x3 only
+  if (FUSE == 2 && a->mode != 0 && a->mode != 3) return DSG_HALO_SKIP;  // TMA-store form: unit-stride outputs only
   p.N = a->n; p.OH = oh; p.OW = ow; p.TW = tw; p.tw_shift = sh; p.TH = th;
   p.tiles_w = ceil_div(ow, tw); p.tiles_h = ceil_div(oh, th * CG);  // a CTA pair stacks its two tiles vertically
   p.cout = a->cout; p.n_blocks = a->cout / BLOCK_N;
@@ -593,6 +610,16 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
       kb += scc[s] / 64;
     }
     k_total = (int64_t)kb * 64;
+  } else if (a->mode == 3) {
+    // 1x1 conv / linear layer: one tap, no halo — the "shortcut panel" group alone.  With K this short the kernel is
+    // all epilogue, which is what the CTA-pair forms (and the eight-warp TMA-store form for N = 64) are good at.
+    p.phases = 1; p.omul = 1;
+    HlGroup& G = p.grp[p.ngroups++];
+    G.map = 0; G.dx = 0; G.dy0 = 0; G.nchunks = cin_chunks; G.ntaps = 1;
+    G.chunk_off = 0; G.transform = 0;
+    G.row_off[0] = 0; G.kb_base[0] = 0;
+    G.bytes = th * tw * 128;
+    k_total = a->cin;
   } else {  // mode 2: four sub-pixel phases, each a 2x2 conv at the input resolution
     p.phases = 4; p.omul = 2;
     for (int j = 0; j < 2; ++j) {
@@ -617,6 +644,7 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
   p.stats = (long long*)a->out_stats;
   p.coef = (const float2*)a->gn_coef; p.cin_main = a->cin; p.IH = a->h; p.IW = a->w;
   p.total_tiles = (int64_t)p.phases * p.N * p.tiles_h * p.tiles_w * p.n_blocks;
+  p.xpose = epi_xpose_enabled() ? 1 : 0;
   if constexpr (FUSE == 2) {
     static_assert(Cfg::STAGE, "no staging buffers in this configuration");
     rc = make_map_a(&maps.o, dense_src(a->out, a->cout, oh, ow), a->n, tw, 32 / tw);
@@ -654,7 +682,8 @@ static int launch_halo(const dsg_conv_args* a, cudaStream_t st) {
 }
 
 int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStream_t st) {
-  if (a->mode != 0 && a->mode != 2) return DSG_HALO_SKIP;
+  if (a->mode != 0 && a->mode != 2 && a->mode != 3) return DSG_HALO_SKIP;
+  if (a->mode == 3 && (!cta_pair || a->csc1 || a->csc2 || !halo_1x1_enabled())) return DSG_HALO_SKIP;
   if (a->gn_coef) {  // fused GroupNorm + SiLU on the input (mode 0 only)
     if (cta_pair) {
       switch (block_n) {
@@ -678,7 +707,8 @@ int launch_halo_conv(const dsg_conv_args* a, int block_n, int cta_pair, cudaStre
         // FUSE = 2: fp16 NHWC output staged in shared memory and written by TMA tensor stores (plain 3x3 convs)
         // — the layers whose main loop is short enough (3x3 over 64 channels, + at most a 64-channel shortcut panel) for
         // the epilogue to pace the kernel; with more K the deeper weight ring of the plain form wins (measured)
-        if (a->mode == 0 && a->out && !a->out_nchw_f32 && a->cin == 64 && a->csc1 + a->csc2 <= 64 && tma_out_enabled())
+        if (a->out && !a->out_nchw_f32 && tma_out_enabled() &&
+            ((a->mode == 0 && a->cin == 64 && a->csc1 + a->csc2 <= 64) || a->mode == 3))
           return launch_halo<64, 2, 2, 2>(a, st);
         return launch_halo<64, 2, 2, 0>(a, st);
       case 128: return launch_halo<128, 2, 2, 0>(a, st);
