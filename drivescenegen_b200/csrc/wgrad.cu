@@ -12,7 +12,9 @@
 //     box at byte offset (dy + 1) * TW * 128 (a multiple of the 1024 B swizzle atom), and
 //   * taps as N atoms — those three shifted views are the three 64-wide "atoms" of ONE N = 192 B operand
 //     (LBO = TW * 128: the atoms overlap in shared memory), so a single tcgen05.mma covers three taps.
-// A = dY (M = 128 output channels, two 64-channel boxes; a 64-channel layer computes 64 don't-care rows),
+// A = dY (M = 128 output channels, two 64-channel boxes; a 64-channel layer instead stacks dY shifted by one pixel in x
+// as its second M atom — a shift of dY by s against the unshifted X is the tap dx = -s — so two of its three column
+// taps share one full-height MMA and the level-0 layers do 2/3 of the tensor work they did with don't-care rows),
 // D[co][(tap, ci)] accumulates in TMEM over a contiguous range of pixel tiles; the pixel axis is split over CTAs
 // (one work item x one split per CTA, one wave) and each CTA stores its fp32 partial tile to a workspace
 // [split][co][tap][ci].  wgrad_reduce_kernel sums the splits in a fixed order (deterministic — no atomics), applies
@@ -50,6 +52,13 @@ struct WgGroup {
   WgBox box[WG_MAX_BOX];
   WgUnit unit[WG_MAX_UNIT];
   int nbox, nunit;
+  // A operand (dY): a_nbox 64-channel boxes = M atoms.  Normally atoms are consecutive channel blocks of one output-channel
+  // block (a_chan = 0, 1; a_dx = 0).  A 64-channel layer has only one: instead of 64 don't-care accumulator rows, its
+  // second atom is the SAME channels shifted by one pixel in x — shifting dY by s against an unshifted X is the tap
+  // dx = -s, so one MMA covers two column taps (tap_hi = the workspace tap column of accumulator rows 64..127, else -1).
+  int a_nbox;
+  int a_chan[2], a_dx[2];
+  int tap_hi;
 };
 struct WgPlan {
   WgGroup grp[WG_MAX_GRP];
@@ -129,7 +138,7 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_holder, 0);
   pdl_sync();  // setup above overlaps the previous kernel's tail
 
-  int stage_bytes_tx = p.a_bytes;
+  int stage_bytes_tx = G.a_nbox * WG_A_BOX;
   for (int b = 0; b < G.nbox; ++b) stage_bytes_tx += G.box[b].bytes;
 
   if (warp == 0) {
@@ -145,8 +154,9 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
       uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes_tx);
-        for (int i = 0; i < p.n_abox; ++i)
-          tma_load_4d(sa + i * WG_A_BOX, &maps.a[phase], &full[stage], (cob * 2 + i) * 64, w0, h0, n);
+        for (int i = 0; i < G.a_nbox; ++i)
+          tma_load_4d(sa + i * WG_A_BOX, &maps.a[phase], &full[stage], (cob * 2 + G.a_chan[i]) * 64, w0 + G.a_dx[i], h0,
+                      n);
         for (int b = 0; b < G.nbox; ++b) {
           const WgBox& B = G.box[b];
           tma_load_4d(sa + p.a_bytes + B.smem_off, &maps.x[B.map], &full[stage], (chunk0 + B.chunk) * 64,
@@ -189,7 +199,8 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
     // ===================================================== epilogue: TMEM -> fp32 workspace partial
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int co = cob * 128 + row;
+    const bool hi = G.tap_hi >= 0 && row >= 64;          // rows 64..127 = the second column tap of a 64-channel layer
+    const int co = G.tap_hi >= 0 ? (row & 63) : cob * 128 + row;
     if (t_begin < t_end) {
       mbar_wait(tfull, 0);
       tc_fence_after();
@@ -199,7 +210,7 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPlan
     for (int u = 0; u < G.nunit; ++u) {
       const WgUnit& U = G.unit[u];
       for (int a = 0; a < U.natoms; ++a) {
-        const int tap = U.tap0 + a * U.tap_step + phase * 4;
+        const int tap = (hi ? G.tap_hi : U.tap0) + a * U.tap_step + phase * 4;
         const int ci = chunk0 * 64 + U.ci0 + a * U.ci_step;
         float* dst = wrow + (int64_t)tap * p.ci + ci;
 #pragma unroll
@@ -374,7 +385,7 @@ static bool wg_geometry(int mode, int n, int h, int w, int cin, int cout, int* t
   const int th = 128 / tw;
   if (gh < th + 2) return false;
   int nchunk, ngroups, phases = 1;
-  if (mode == 0) { nchunk = (cin % 128 == 0) ? 2 : 1; ngroups = 3; }
+  if (mode == 0) { nchunk = (cin % 128 == 0) ? 2 : 1; ngroups = cout == 64 ? 2 : 3; }
   else if (mode == 3) { nchunk = (cin % 256 == 0) ? 4 : ((cin % 128 == 0) ? 2 : 1); ngroups = 1; }
   else if (mode == 1) { nchunk = 1; ngroups = 3; }
   else { nchunk = (cin % 128 == 0) ? 2 : 1; ngroups = 2; phases = 4; }
@@ -449,14 +460,32 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
   if (a->mode == 0) {
     p.ktaps = 9;
     p.ci_per_item = nchunk * 64;
-    p.ngroups = 3;
     const int box_bytes = (th + 2) * row_bytes;
-    for (int dx = -1; dx <= 1; ++dx) {
-      WgGroup& G = p.grp[dx + 1];
-      G.nbox = nchunk; G.nunit = nchunk;
-      for (int c = 0; c < nchunk; ++c) {
-        G.box[c] = WgBox{0, c, dx, -1, box_bytes, c * box_bytes};
-        G.unit[c] = WgUnit{c * box_bytes, 3, row_bytes, c * 256, dx + 1, 3, c * 64, 0};
+    if (a->cout == 64) {
+      // two work-item kinds instead of three: {dx = -1, 0} as the two M atoms of one MMA (dY shifted by +1 / 0 against
+      // the unshifted X box), and dx = +1 alone (dY shifted by -1; its second atom is don't-care as before)
+      p.ngroups = 2;
+      for (int g = 0; g < 2; ++g) {
+        WgGroup& G = p.grp[g];
+        G.nbox = nchunk; G.nunit = nchunk;
+        for (int c = 0; c < nchunk; ++c) {
+          G.box[c] = WgBox{0, c, 0, -1, box_bytes, c * box_bytes};
+          G.unit[c] = WgUnit{c * box_bytes, 3, row_bytes, c * 256, g == 0 ? 0 : 2, 3, c * 64, 0};
+        }
+        G.a_nbox = g == 0 ? 2 : 1;
+        G.a_chan[0] = G.a_chan[1] = 0;
+        G.a_dx[0] = g == 0 ? 1 : -1; G.a_dx[1] = 0;
+        G.tap_hi = g == 0 ? 1 : -1;
+      }
+    } else {
+      p.ngroups = 3;
+      for (int dx = -1; dx <= 1; ++dx) {
+        WgGroup& G = p.grp[dx + 1];
+        G.nbox = nchunk; G.nunit = nchunk;
+        for (int c = 0; c < nchunk; ++c) {
+          G.box[c] = WgBox{0, c, dx, -1, box_bytes, c * box_bytes};
+          G.unit[c] = WgUnit{c * box_bytes, 3, row_bytes, c * 256, dx + 1, 3, c * 64, 0};
+        }
       }
     }
     rc = make_map_px(&maps.a[0], dense_src(a->dy, a->cout, gh, gw), a->n, tw, th);
@@ -531,6 +560,15 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
     if (p.phases == 1) maps.a[i] = maps.a[0];
   for (int i = 1; i < WG_MAX_MAPS; ++i)
     if (a->mode != 1) maps.x[i] = maps.x[0];
+  for (int g = 0; g < p.ngroups; ++g) {
+    WgGroup& G = p.grp[g];
+    if (G.a_nbox == 0) {   // the usual A operand: consecutive 64-channel blocks of the output-channel block, unshifted
+      G.a_nbox = p.n_abox;
+      G.a_chan[0] = 0; G.a_chan[1] = 1;
+      G.a_dx[0] = G.a_dx[1] = 0;
+      G.tap_hi = -1;
+    }
+  }
   p.ci_groups = a->cin / p.ci_per_item;
   int b_bytes = 0;
   for (int g = 0; g < p.ngroups; ++g) {
@@ -538,6 +576,7 @@ int dsg_conv_wgrad(const dsg_wgrad_args* a, void* stream) {
     for (int b = 0; b < p.grp[g].nbox; ++b) bb += p.grp[g].box[b].bytes;
     if (bb > b_bytes) b_bytes = bb;
   }
+  if (a->mode == 0 && a->cout == 64) p.a_bytes = 2 * WG_A_BOX;   // the pair kind loads two (shifted) A boxes
   p.stage_bytes = p.a_bytes + b_bytes;
   // a 64-channel layer's second (don't-care) M atom reads 16 KB past its single A box: keep that inside the stage
   if (p.n_abox == 1 && p.stage_bytes < 2 * WG_A_BOX) p.stage_bytes = 2 * WG_A_BOX;
