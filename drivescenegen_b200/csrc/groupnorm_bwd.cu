@@ -12,7 +12,11 @@
 // in a fixed layout; gn_bwd_apply_kernel (reads da, x again) sums the chunk partials in a fixed order — deterministic,
 // no atomics — and writes dx.  Both evaluate g with the SAME fp16x2 instruction sequence (one MUFU op per PAIR of
 // elements, silu_grad_h2): the fp32 form made both passes issue-bound at ~0.55 of the HBM rate, and storing g after the
-// first pass instead (measured) costs a sixth pass over the tensor for nothing — the kernels are memory-bound now, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
+// first pass instead (measured) costs a sixth pass over the tensor for nothing — the kernels are memory-bound now.
+// Also measured and dropped (profiles/README.md, r2m): both passes as ONE persistent launch interleaved by sample group so
+// that pass 2 would find x / dy in the L2 — with the 18 work items per sample and pass that the partial-sum layout allows,
+// half of the resident CTAs sit waiting for their group's pass 1 in every wave (2.3x slower); enough items per sample to
+// fill a wave with ONE sample's pass would make the per-item prologue (statistics -> mean / rstd) dominate, optionally (+ an addend tensor: the ResnetBlock shortcut's gradient) (+ the previous
 // content of the destination: a tensor with two consumers), split over the two concatenated sources.  It can also emit
 // per-CTA column sums of what it wrote (the time-embedding / conv1-bias gradient of a ResnetBlock).
 // Forward statistics come from the same int64 per-channel totals the forward used (groupnorm.cu).
@@ -98,10 +102,10 @@ __device__ __forceinline__ __half2 silu_grad_h2(__half2 h) {
 // combined, sum g * xh = rstd * (sum g x - mean * sum g), which keeps the per-thread state small).
 constexpr int GB_ILP = 4;
 template <bool ACT>
-__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwdArgs a) {
+__device__ __forceinline__ void gn_bwd_stats_body(const GnBwdArgs& a, const int n, const int chunk,
+                                                  const int64_t px_per_block) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
-  const int n = blockIdx.y, chunk = blockIdx.x;
   __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS];
   __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
   __shared__ float s_part[2][GB_THREADS * 8];
@@ -112,11 +116,10 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   const __half* src = from1 ? a.x1 : a.x2;
   const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
   const int64_t base_px = (int64_t)n * a.hw;
-  const int64_t p_begin = (int64_t)chunk * a.px_per_block;
-  int64_t p_end = p_begin + a.px_per_block;
+  const int64_t p_begin = (int64_t)chunk * px_per_block;
+  int64_t p_end = p_begin + px_per_block;
   if (p_end > a.hw) p_end = a.hw;
   int64_t p = p_begin + prow;
-  pdl_sync();
   if (ACT) gn_moments(a, n, s_mean, s_rstd, s_t);
   if (active) {
     float gah[8], ybh[8], sA[8], sB[8];   // y / 2 = x * gah + ybh
@@ -183,6 +186,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
     reinterpret_cast<float2*>(o)[c] = make_float2(tA, tB);
   }
 }
+template <bool ACT>
+__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwdArgs a) {
+  pdl_sync();
+  gn_bwd_stats_body<ACT>(a, blockIdx.y, blockIdx.x, a.px_per_block);
+}
 
 // Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1).
 #ifndef GB_APPLY_CTAS
@@ -191,10 +199,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
 #ifndef GB_APPLY_ILP
 #define GB_APPLY_ILP 3
 #endif
-__global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+template <int ILP>
+__device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int n, const int part, const int nparts,
+                                                  const int64_t px_per_block) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
   const int ppi = GB_THREADS / V;
-  const int n = blockIdx.y;
   __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS], s_m1[GB_MAX_GROUPS], s_m2[GB_MAX_GROUPS];
   __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
   __shared__ float s_part[2][GB_THREADS * 8];  // prologue: gamma * A / gamma * B per channel; epilogue: column sums
@@ -207,13 +216,11 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
   const int accum = from1 ? a.acc1 : a.acc2;
   const int cs = from1 ? a.c1 : a.c2, co = from1 ? ch0 : ch0 - a.c1;
   const int64_t base_px = (int64_t)n * a.hw;
-  const int64_t p_begin = (int64_t)blockIdx.x * a.px_per_block;
-  int64_t p_end = p_begin + a.px_per_block;
+  const int64_t p_begin = (int64_t)part * px_per_block;
+  int64_t p_end = p_begin + px_per_block;
   if (p_end > a.hw) p_end = a.hw;
-  constexpr int ILP = GB_APPLY_ILP;
   int64_t p = p_begin + prow;
   const bool want_osum = (from1 ? a.osum1 : a.osum2) != nullptr;
-  pdl_sync();
   gn_moments(a, n, s_mean, s_rstd, s_t);
   {
     const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
@@ -221,12 +228,12 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
     for (int c = threadIdx.x; c < C; c += GB_THREADS) {
       float tA = 0.f, tBx = 0.f;
       for (int k = 0; k < a.chunks; ++k) {  // fixed order
-        const float2 t = reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2)[c];
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2) + c);   // written by other SMs
         tA += t.x; tBx += t.y;
       }
       const int g = c / cpg;
       const float tB = s_rstd[g] * (tBx - s_mean[g] * tA);  // sum g * xh
-      if (blockIdx.x == 0) reinterpret_cast<float2*>(red)[c] = make_float2(tA, tB);
+      if (part == 0) reinterpret_cast<float2*>(red)[c] = make_float2(tA, tB);
       const float gm = a.gamma[c];
       s_part[0][c] = gm * tA;
       s_part[1][c] = gm * tB;
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
       for (int j = 0; j < 8; ++j) s_part[0][prow * C + ch0 + j] = cs_acc[j];
     }
     __syncthreads();
-    float* o = a.colsum + ((int64_t)n * gridDim.x + blockIdx.x) * C;
+    float* o = a.colsum + ((int64_t)n * nparts + part) * C;
     for (int c = threadIdx.x; c < C; c += GB_THREADS) {
       float t = 0.f;
       for (int r = 0; r < ppi; ++r) t += s_part[0][r * C + c];
@@ -331,9 +338,14 @@ __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel
       const int cw = c < a.c1 ? a.c1 : a.c2, cc = c < a.c1 ? c : c - a.c1;
       float t = 0.f;
       for (int r = 0; r < ppi; ++r) t += s_part[1][r * C + c];
-      base[((int64_t)n * gridDim.x + blockIdx.x) * cw + cc] = t;
+      base[((int64_t)n * nparts + part) * cw + cc] = t;
     }
   }
+}
+
+__global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
+  pdl_sync();
+  gn_bwd_apply_body<GB_APPLY_ILP>(a, blockIdx.y, blockIdx.x, gridDim.x, a.px_per_block);
 }
 
 // column sums of an fp16 [rows][C] tensor: per-block partials [blocks][C] (fp32), fixed order inside a block
@@ -433,12 +445,6 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   a.inv_cnt_s = 1.0 / 16777216.0 / ((double)hw * (double)(C / groups));
   a.inv_cnt_q = 1.0 / 1048576.0 / ((double)hw * (double)(C / groups));
   cudaStream_t st = (cudaStream_t)stream;
-  a.px_per_block = ceil_div64(hw, chunks);
-  if (act)
-    launch_k(gn_bwd_stats_kernel<true>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
-  else
-    launch_k(gn_bwd_stats_kernel<false>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
-  DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
   int64_t ctas = parts;
   if (ctas == 0) {
     ctas = (148 * 4) / n;
@@ -446,6 +452,12 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
     const int64_t max_ctas = ceil_div64(hw, 32);
     if (ctas > max_ctas) ctas = max_ctas;
   }
+  a.px_per_block = ceil_div64(hw, chunks);
+  if (act)
+    launch_k(gn_bwd_stats_kernel<true>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
+  else
+    launch_k(gn_bwd_stats_kernel<false>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
+  DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
   a.px_per_block = ceil_div64(hw, ctas);
   launch_k(gn_bwd_apply_kernel, dim3((unsigned)ctas, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/apply");
