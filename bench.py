@@ -2,19 +2,30 @@
 """bench.py — denoise-steps/s on 256x256x3 rasters (BASELINE.json configs[1]) and the U-Net conv roofline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--size S]
+                    [--scheduler ddim --size 512 --batch 8]   (configs[3])      [--workload train]   (configs[2] alone)
 
 One "step" = one DDPM denoising step (U-Net forward + scheduler.step) over a batch of B=16 synthetic 256x256x3
 samples with random-init weights of the reference architecture (DriveSceneGen/scripts/train.py:39-57).
-  value     sample-steps/s (= B*K/time), inputs resident in HBM, CUDA events, max over ranks; N>1 = N independent
-            replicas (sampling never communicates: SURVEY.md §8e), weak scaling.
-  e2e       same metric through DenoiseSession.run_from_host: every step copies that step's variance noise from
-            pinned host memory to the device and reads the new sample back to pinned host memory; the copies run
-            on their own streams beside the next step's compute (serial copy->step->copy->sync time also reported).
-  roofline  the tcgen05 implicit-GEMM conv kernel: algorithmic conv/linear FLOPs of one step (reference op count)
-            / summed CUDA-event duration of those launches in an eager, per-launch-timed replay of the same step
-            (per-launch median of 5 replays).
+  value       sample-steps/s (= B*K/time), inputs resident in HBM, CUDA events, max over ranks; N>1 = N independent
+              replicas (sampling never communicates: SURVEY.md §8e), weak scaling.  One CUDA-graph launch per step.
+  e2e         same metric through DenoiseSession.run_from_host: every step copies that step's variance noise from
+              pinned host memory to the device and reads the new sample back to pinned host memory; the copies run
+              on their own streams beside the next step's compute (serial copy->step->copy->sync time also reported).
+  e2e_pipeline  the reference-facing call itself, DDPMPipeline.__call__ (training_pipeline.py:26-32, generation.py:14),
+              K steps, numpy out: with generator=None and with a CPU generator (upstream RNG rule: host draws).
+  roofline    the tcgen05 implicit-GEMM conv kernels: algorithmic conv/linear FLOPs of one step (reference op count)
+              / summed CUDA-event duration of those launches in an eager, per-launch-timed replay of the same step
+              (per-launch median of 5 replays); `frac_executed` counts the MACs really executed (sub-pixel upsample
+              convs run 4/9 of the reference's); `traffic` = DRAM bytes per launch from an `ncu --set full` capture of the
+              commit named in `traffic_source` (tools/conv_traffic.py).
+  kernels     per-kernel-class records (conv, conv_cout64, conv_upsample, gn_apply, conv_in/out, attention, sched_step):
+              algorithmic work, executed work, event time, fraction of the measured peak.
+  whole_step  U-Net forward FLOPs / ms_per_step against the tensor peak (GroupNorm, attention, scheduler included).
+  train       configs[2] in the same line: 256x256x3 training step (fwd + bwd + clip + AdamW), batch 32 per GPU, one
+              flat-buffer gradient all-reduce per step when N > 1 (overlapped with the backward), with its own roofline
+              (weight-gradient kernel), per-class records and whole-step fraction.
   cpu_baseline / --impl reference: the CPU oracle (plain PyTorch fp32 restatement of the reference path) on this
-            box's host cores, bounded sample (batch 2).
+              box's host cores, bounded sample (batch 2).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -249,13 +260,13 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
     ar_ms = None
     if world > 1:
         import torch.distributed as dist
-        flat = acc._flat_grad_of(model)
-        if flat is not None:
+        fg = getattr(model, "_flat_grads", None)
+        if fg is not None:
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(5):
-                acc._allreduce_grads()
+                acc._reduce_mean(fg.flat[0])
             a1.record()
             barrier()
             ar_ms = a0.elapsed_time(a1) / 5

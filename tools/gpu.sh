@@ -13,6 +13,8 @@
 #   full-train <regex> <name>   same inside the training step
 #                        (NCU_EXTRA="-c 12" in the environment limits the number of profiled launches)
 #   sweep                tools/op_sweep.py --raster
+#   traffic <full-stage name> <B> <S> <commit>   conv DRAM traffic json for bench.py's roofline.traffic
+#   parity               full -m gpu suite with -s, keeping the [parity] tolerance lines
 # Stages are separated by `--`:  bash tools/gpu.sh r2a test -- bench --steps 40 -- launches
 TAG=$1; shift
 O=gpurun_out/$TAG
@@ -43,6 +45,10 @@ run_stage() {
       ncu -i $O/$name.ncu-rep --page raw --csv > $O/${name}_raw.csv 2>/dev/null
       python tools/ncu_raw_summary.py $O/${name}_raw.csv > $O/${name}_summary.txt 2>&1 ;;
     sweep) timeout 600 python tools/op_sweep.py --raster --out $O/op_sweep.json > $O/op_sweep.log 2>&1 ;;
+    traffic)   # traffic <name of a finished `full` stage> <batch> <size> <commit>: profiles/conv_traffic_b<B>_<S>.json
+      python tools/conv_traffic.py $O/${1}_raw.csv $2 $3 $4 $O/conv_traffic_b${2}_${3}.json > $O/conv_traffic_${2}_${3}.log 2>&1 ;;
+    parity)    # the tolerance lines the parity tests print
+      timeout 1800 python -m pytest tests -m gpu -q -s 2>&1 | grep -a "\[parity\]\|reference scripts\]\| passed\| failed" > $O/parity_lines.txt ;;
     *) echo "unknown stage $s" >&2 ;;
   esac
 }
