@@ -199,7 +199,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
 #ifndef GB_APPLY_ILP
 #define GB_APPLY_ILP 3
 #endif
-template <int ILP>
+// ADD / ACC / CSUM / OSUM: whether the call has an addend, accumulates into a destination, wants the column sums of the
+// GroupNorm term / of the stored values.  Compile-time: the kernel is instruction-issue-bound (ncu: 61 % of all issue
+// slots at 23 % occupancy, profiles/r2o_ncu_full_gn_bwd_streamed_vs_register.txt), and the unpack + add sequences of
+// the absent operands were a quarter of the inner loop.
+template <int ILP, bool ADD, bool ACC, bool CSUM, bool OSUM>
 __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int n, const int part, const int nparts,
                                                   const int64_t px_per_block) {
   const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
@@ -220,7 +224,7 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
   int64_t p_end = p_begin + px_per_block;
   if (p_end > a.hw) p_end = a.hw;
   int64_t p = p_begin + prow;
-  const bool want_osum = (from1 ? a.osum1 : a.osum2) != nullptr;
+  const bool want_osum = OSUM && (from1 ? a.osum1 : a.osum2) != nullptr;
   gn_moments(a, n, s_mean, s_rstd, s_t);
   {
     const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
@@ -265,16 +269,17 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
       qc[j] = rs * (mu * rs * s_m2[g] - s_m1[g]);
     }
     for (; p < p_end; p += (int64_t)ppi * ILP) {
-      uint4 rx[ILP], rd[ILP], ra[ILP], ro[ILP];
+      uint4 rx[ILP], rd[ILP], ra[ADD ? ILP : 1], ro[ACC ? ILP : 1];
 #pragma unroll
       for (int u = 0; u < ILP; ++u) {
-        ra[u] = make_uint4(0, 0, 0, 0); ro[u] = make_uint4(0, 0, 0, 0);
+        if (ADD) ra[u] = make_uint4(0, 0, 0, 0);
+        if (ACC) ro[u] = make_uint4(0, 0, 0, 0);
         const int64_t pp = p + (int64_t)u * ppi;
         if (pp < p_end) {
           rx[u] = ldg_nc_v4(src + (base_px + pp) * cs + co);
           rd[u] = ldg_nc_v4(a.dy + (base_px + pp) * C + ch0);
-          if (a.addend) ra[u] = ldg_nc_v4(a.addend + (base_px + pp) * C + ch0);
-          if (accum) ro[u] = *reinterpret_cast<const uint4*>(dst + (base_px + pp) * cs + co);
+          if (ADD) ra[u] = ldg_nc_v4(a.addend + (base_px + pp) * C + ch0);
+          if (ACC && accum) ro[u] = *reinterpret_cast<const uint4*>(dst + (base_px + pp) * cs + co);
         }
       }
 #pragma unroll
@@ -282,7 +287,9 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
         const int64_t pp = p + (int64_t)u * ppi;
         if (pp < p_end) {
           float fx[8], fd[8], fa[8], fo[8], r[8];
-          unpack8(rx[u], fx); unpack8(ra[u], fa); unpack8(ro[u], fo);
+          unpack8(rx[u], fx);
+          if (ADD) unpack8(ra[u], fa);
+          if (ACC) unpack8(ro[u], fo);
           if (a.act) {   // g = dy * SiLU'(y): fp16x2, one MUFU per pair — bit-identical to what pass 1 summed
             __half2* hd = reinterpret_cast<__half2*>(&rd[u]);
 #pragma unroll
@@ -296,8 +303,10 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float d = fmaf(ga[j], fd[j], fmaf(pc[j], fx[j], qc[j]));
-            cs_acc[j] += d;
-            r[j] = (d + fa[j]) + fo[j];
+            if (CSUM) cs_acc[j] += d;
+            r[j] = d;
+            if (ADD) r[j] += fa[j];       // same order of additions as before: (d + addend) + previous content
+            if (ACC) r[j] += fo[j];
           }
           const uint4 packed = pack8(r);
           stg_v4(dst + (base_px + pp) * cs + co, packed);
@@ -311,7 +320,7 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
       }
     }
   }
-  if (a.colsum) {
+  if (CSUM) {
     __syncthreads();
     if (active) {
 #pragma unroll
@@ -325,7 +334,7 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
       o[c] = t;
     }
   }
-  if (a.osum1 || a.osum2) {
+  if (OSUM) {
     __syncthreads();
     if (active) {
 #pragma unroll
@@ -343,9 +352,23 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
   }
 }
 
+template <bool ADD, bool ACC, bool CSUM, bool OSUM>
 __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
   pdl_sync();
-  gn_bwd_apply_body<GB_APPLY_ILP>(a, blockIdx.y, blockIdx.x, gridDim.x, a.px_per_block);
+  gn_bwd_apply_body<GB_APPLY_ILP, ADD, ACC, CSUM, OSUM>(a, blockIdx.y, blockIdx.x, gridDim.x, a.px_per_block);
+}
+typedef void (*GnBwdApplyFn)(const GnBwdArgs);
+template <int I>
+static GnBwdApplyFn gn_bwd_apply_variant() {
+  return gn_bwd_apply_kernel<(I & 1) != 0, (I & 2) != 0, (I & 4) != 0, (I & 8) != 0>;
+}
+static GnBwdApplyFn gn_bwd_apply_pick(bool add, bool acc, bool csum, bool osum) {
+  static const GnBwdApplyFn table[16] = {
+      gn_bwd_apply_variant<0>(),  gn_bwd_apply_variant<1>(),  gn_bwd_apply_variant<2>(),  gn_bwd_apply_variant<3>(),
+      gn_bwd_apply_variant<4>(),  gn_bwd_apply_variant<5>(),  gn_bwd_apply_variant<6>(),  gn_bwd_apply_variant<7>(),
+      gn_bwd_apply_variant<8>(),  gn_bwd_apply_variant<9>(),  gn_bwd_apply_variant<10>(), gn_bwd_apply_variant<11>(),
+      gn_bwd_apply_variant<12>(), gn_bwd_apply_variant<13>(), gn_bwd_apply_variant<14>(), gn_bwd_apply_variant<15>()};
+  return table[(add ? 1 : 0) | (acc ? 2 : 0) | (csum ? 4 : 0) | (osum ? 8 : 0)];
 }
 
 // column sums of an fp16 [rows][C] tensor: per-block partials [blocks][C] (fp32), fixed order inside a block
@@ -459,7 +482,9 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
     launch_k(gn_bwd_stats_kernel<false>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
   a.px_per_block = ceil_div64(hw, ctas);
-  launch_k(gn_bwd_apply_kernel, dim3((unsigned)ctas, n), dim3(GB_THREADS), 0, st, a);
+  launch_k(gn_bwd_apply_pick(addend != nullptr, acc1 != 0 || (acc2 != 0 && c2 > 0), colsum != nullptr,
+                             osum1 != nullptr || osum2 != nullptr),
+           dim3((unsigned)ctas, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/apply");
   return DSG_OK;
 }
