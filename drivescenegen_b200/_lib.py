@@ -118,7 +118,7 @@ SIGNATURES = {
     "dsg_attention": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _p]),
     "dsg_attention_ex": (C.c_int, [_p, _p, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     # ---- training path
-    "dsg_pack_job_chunks": (_i64, [_i64, _i64]),
+    "dsg_pack_job_blocks": (_i64, [_i32, _i32, _i32, _i32]),
     "dsg_pack_conv_weights_batched": (C.c_int, [_p, _i32, _i64, _p]),
     "dsg_packed_k_dgrad": (_i64, [_i32, _i32]),
     "dsg_packed_rows_dgrad": (_i64, [_i32, _i32]),

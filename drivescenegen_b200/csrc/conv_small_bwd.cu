@@ -113,11 +113,23 @@ __global__ void __launch_bounds__(SB_THREADS) small_wgrad_kernel(const __half* _
     }
     __syncthreads();
     const __half2* wp = reinterpret_cast<const __half2*>(wide + (((int64_t)nn * h + y) * w) * wc) + c_t;
+    // the next step's four pixels are in flight while this step's 216 FMAs run (the loop was latency-bound: one round
+    // trip to HBM per 4 pixels with nothing to overlap it inside the warp)
+    __half2 nxt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int xx = slice * U + u;
+      nxt[u] = xx < w ? wp[(int64_t)xx * wc2] : __float2half2_rn(0.f);
+    }
     for (int x0 = slice * U; x0 < w; x0 += nslices * U) {
       float2 a[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        a[u] = x0 + u < w ? __half22float2(wp[(int64_t)(x0 + u) * wc2]) : make_float2(0.f, 0.f);
+      for (int u = 0; u < U; ++u) a[u] = __half22float2(nxt[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int xx = x0 + nslices * U + u;
+        nxt[u] = xx < w ? wp[(int64_t)xx * wc2] : __float2half2_rn(0.f);
+      }
 #pragma unroll
       for (int c = 0; c < NC; ++c)
 #pragma unroll

@@ -327,31 +327,6 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(int mode, const float*
   }
 }
 
-// Every conv weight of the model in ONE launch (a training step re-packs all of them after each optimizer step):
-// jobs[] lives in device memory; chunk c (PACK_CHUNK consecutive packed elements) belongs to the job with the largest
-// chunk_begin <= c.
-constexpr int PACK_CHUNK = 2048;
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dsg_pack_job* __restrict__ jobs, int njobs) {
-  int lo = 0, hi = njobs - 1;
-  const int64_t c = blockIdx.x;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].chunk_begin <= c) lo = mid; else hi = mid - 1;
-  }
-  const dsg_pack_job j = jobs[lo];
-  const int64_t total = j.rows * j.k_total;
-  const int64_t base = (c - j.chunk_begin) * PACK_CHUNK;
-  __half* out = (__half*)j.out;
-#pragma unroll
-  for (int u = 0; u < PACK_CHUNK / 256; ++u) {
-    const int64_t i = base + u * 256 + threadIdx.x;
-    if (i < total) {
-      const int64_t r = i / j.k_total, k = i - r * j.k_total;
-      out[i] = __float2half_rn(pack_value(j.mode, j.w, j.cout, j.cin, j.w_sc, j.csc, r, k));
-    }
-  }
-}
-
 static int build_plan(const dsg_conv_args* a, IgPlan& p) {
   memset(&p, 0, sizeof(p));
   DSG_CHECK_ARG(a->mode >= 0 && a->mode <= 4, "dsg_conv: bad mode %d", a->mode);
@@ -514,16 +489,6 @@ int dsg_pack_conv_weight(int32_t mode, const float* w_oihw, int32_t cout, int32_
   pack_weight_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mode, w_oihw, cout, cin, w_sc, csc,
                                                                         (__half*)wpacked, k_total, rows);
   DSG_CUDA_LAUNCH_CHECK("dsg_pack_conv_weight");
-  return DSG_OK;
-}
-
-int64_t dsg_pack_job_chunks(int64_t rows, int64_t k_total) { return ceil_div64(rows * k_total, PACK_CHUNK); }
-
-int dsg_pack_conv_weights_batched(const dsg_pack_job* jobs_dev, int32_t njobs, int64_t total_chunks, void* stream) {
-  DSG_CHECK_ARG(jobs_dev && njobs >= 1 && total_chunks >= 1 && total_chunks < (int64_t)1 << 31,
-                "dsg_pack_conv_weights_batched: bad args");
-  pack_weights_batched_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
-  DSG_CUDA_LAUNCH_CHECK("dsg_pack_conv_weights_batched");
   return DSG_OK;
 }
 

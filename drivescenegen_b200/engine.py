@@ -198,20 +198,30 @@ class UNetEngine:
         if not self._jobs:
             return
         if self._jobs != self._jobs_uploaded:
-            arr = (_lib.PackJob * len(self._jobs))()
-            chunk = 0
-            for j, (mode, cout, cin, csc, w, wsc, out, k, rows) in zip(arr, self._jobs):
+            batched, single, chunk = [], [], 0
+            for job in self._jobs:
+                mode, cout, cin, csc = job[:4]
+                nb = int(self.lib.dsg_pack_job_blocks(mode, cout, cin, csc))
+                if nb < 0:          # a source row too wide for the shared-memory staged form: element-wise kernel
+                    single.append(job)
+                else:
+                    batched.append((job, chunk))
+                    chunk += nb
+            arr = (_lib.PackJob * max(len(batched), 1))()
+            for j, ((mode, cout, cin, csc, w, wsc, out, k, rows), begin) in zip(arr, batched):
                 j.mode, j.cout, j.cin, j.csc = mode, cout, cin, csc
                 j.w, j.w_sc, j.out = w, (wsc or None), out
-                j.k_total, j.rows, j.chunk_begin = k, rows, chunk
-                chunk += int(self.lib.dsg_pack_job_chunks(rows, k))
+                j.k_total, j.rows, j.chunk_begin = k, rows, begin
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             self._jobs_dev = raw.to(self.device)
-            self._jobs_chunks = chunk
+            self._jobs_blocks, self._jobs_batched, self._jobs_single = chunk, len(batched), single
             self._jobs_uploaded = list(self._jobs)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        check(self.lib.dsg_pack_conv_weights_batched(self._jobs_dev.data_ptr(), len(self._jobs), self._jobs_chunks, st),
-              "pack weights (batched)")
+        if self._jobs_batched:
+            check(self.lib.dsg_pack_conv_weights_batched(self._jobs_dev.data_ptr(), self._jobs_batched,
+                                                         self._jobs_blocks, st), "pack weights (batched)")
+        for mode, cout, cin, csc, w, wsc, out, k, rows in self._jobs_single:
+            check(self.lib.dsg_pack_conv_weight(mode, w, cout, cin, wsc or None, csc, out, st), "pack weight")
 
     def _weight_buf(self, name: str, numel: int, dtype) -> torch.Tensor:
         """Packed-weight buffers keep their address across re-packs (a training step re-packs every step, and the

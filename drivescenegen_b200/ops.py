@@ -146,6 +146,41 @@ def group_norm(x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
     return y
 
 
+def pack_conv_weights_batched(jobs):
+    """jobs: [(mode, w fp32 OIHW on the device, w_sc or None), ...] -> list of packed h16 [rows, k] tensors, all packed by
+    ONE launch of the shared-memory staged kernel (pack_weights.cu)."""
+    lib = _lib.load()
+    arr = (_lib.PackJob * len(jobs))()
+    outs, keep, begin = [], [], 0
+    for j, (mode, w, w_sc) in zip(arr, jobs):
+        _cuda(w, w_sc)
+        w = w.float().contiguous()
+        cout, cin = w.shape[0], w.shape[1]
+        csc = 0
+        if w_sc is not None:
+            w_sc = w_sc.float().reshape(cout, -1).contiguous()
+            csc = w_sc.shape[1]
+        if mode >= 10:
+            k, rows = lib.dsg_packed_k_dgrad(mode - 10, cout), lib.dsg_packed_rows_dgrad(mode - 10, cin)
+        else:
+            k, rows = lib.dsg_packed_k(mode, cin, csc), lib.dsg_packed_rows(mode, cout)
+        out = torch.empty((rows, k), dtype=torch.float16, device=w.device)
+        nb = int(lib.dsg_pack_job_blocks(mode, cout, cin, csc))
+        if nb < 0:
+            raise DsgError("pack_conv_weights_batched: layer too wide for the staged kernel")
+        j.mode, j.cout, j.cin, j.csc = mode, cout, cin, csc
+        j.w, j.w_sc, j.out = w.data_ptr(), _p(w_sc), out.data_ptr()
+        j.k_total, j.rows, j.chunk_begin = k, rows, begin
+        begin += nb
+        outs.append(out)
+        keep.extend([w, w_sc])
+    dev = outs[0].device
+    jobs_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    check(lib.dsg_pack_conv_weights_batched(jobs_dev.data_ptr(), len(jobs), begin, _st(outs[0])), "pack (batched)")
+    torch.cuda.current_stream(dev).synchronize()   # jobs_dev / keep must outlive the launch
+    return outs
+
+
 def pack_conv_weight(mode: int, w, w_sc=None):
     _cuda(w, w_sc)
     lib = _lib.load()

@@ -204,9 +204,11 @@ int dsg_gn_coef(int32_t c1, const void* stats1, int32_t c2, const void* stats2, 
 /* K-extent (in fp16 elements per output channel row) and row count of the packed weight for a mode. */
 int64_t dsg_packed_k(int32_t mode, int32_t cin, int32_t csc);
 int64_t dsg_packed_rows(int32_t mode, int32_t cout);
-/* All conv weights of a model in one launch.  jobs_dev: DEVICE array of njobs entries, each describing one
- * dsg_pack_conv_weight call (same field meaning), sorted by chunk_begin = the running sum of
- * dsg_pack_job_chunks(rows, k_total) over the preceding jobs; total_chunks = that sum over all jobs. */
+/* All conv weights of a model in one launch, staged through shared memory (pack_weights.cu; bit-identical to
+ * dsg_pack_conv_weight).  jobs_dev: DEVICE array of njobs entries, each describing one dsg_pack_conv_weight call (same
+ * field meaning), sorted by chunk_begin = the running sum of dsg_pack_job_blocks(mode, cout, cin, csc) over the
+ * preceding jobs; total_blocks = that sum over all jobs.  dsg_pack_job_blocks returns -1 for a layer too wide for the
+ * staged form (its source row exceeds 40 KB): pack that one with dsg_pack_conv_weight. */
 typedef struct dsg_pack_job {
   int32_t mode, cout, cin, csc;
   const float* w;
@@ -214,8 +216,8 @@ typedef struct dsg_pack_job {
   void* out;
   int64_t k_total, rows, chunk_begin;
 } dsg_pack_job;
-int64_t dsg_pack_job_chunks(int64_t rows, int64_t k_total);
-int dsg_pack_conv_weights_batched(const dsg_pack_job* jobs_dev, int32_t njobs, int64_t total_chunks, void* stream);
+int64_t dsg_pack_job_blocks(int32_t mode, int32_t cout, int32_t cin, int32_t csc);
+int dsg_pack_conv_weights_batched(const dsg_pack_job* jobs_dev, int32_t njobs, int64_t total_blocks, void* stream);
 /* Data-gradient ("dgrad") packings: dsg_pack_conv_weight modes 10..13 take the SAME fp32 OIHW weight as modes 0..3
  * (cout / cin are the forward conv's) and produce the weights of the conv that maps the OUTPUT gradient to the INPUT
  * gradient: 10 -> run dsg_conv mode 0 (cin' = cout, cout' = cin), 11 -> mode 2 over the low-resolution gradient,

@@ -312,3 +312,24 @@ def test_igemm_halo_cta_pair(case):
             assert torch.equal(again, two) and torch.equal(st5, st4)
         else:
             assert torch.equal(st1, st4)
+
+
+def test_batched_weight_pack_is_bit_identical_to_the_single_job_kernel():
+    """pack_weights.cu (one launch for every layer, staged through shared memory) against igemm.cu::pack_weight_kernel
+    (element-wise gather), every packing mode, ragged channel counts, with and without the 1x1 shortcut panel."""
+    from drivescenegen_b200 import ops
+    d = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21)
+    jobs = []
+    for cout, cin in ((64, 64), (72, 40), (136, 200), (16, 64), (512, 1024)):
+        w3 = torch.randn(cout, cin, 3, 3, generator=g).to(d)
+        w1 = torch.randn(cout, cin, 1, 1, generator=g).to(d)
+        for mode in (0, 1, 2, 10, 11, 12):
+            jobs.append((mode, w3, None))
+        jobs.append((0, w3, torch.randn(cout, 48, generator=g).to(d)))
+        for mode in (3, 13):
+            jobs.append((mode, w1, None))
+    got = ops.pack_conv_weights_batched(jobs)
+    for (mode, w, w_sc), out in zip(jobs, got):
+        want = ops.pack_conv_weight(mode, w, w_sc)
+        assert out.shape == want.shape and torch.equal(out, want), (mode, tuple(w.shape))
