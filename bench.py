@@ -236,17 +236,17 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    n0 = _lib.launch_count()
     for _ in range(W):
         step(False)
-    per_step_launches = (_lib.launch_count() - n0) // W
     barrier()
     sampler = ClockSampler(dev.index) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _lib.launch_count()   # kernels of the K timed steps (graph replays report their kernel count to the library)
     e0.record()
     for _ in range(K):
         step(False)
     e1.record()
+    timed_launches = _lib.launch_count() - n0
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
@@ -358,7 +358,7 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
                        "64 % of the bytes) is issued from inside the backward pass and runs under the down path's "
                        "backward, the head follows when the backward returns"},
             "param_checksum": checksum,
-            "gpu_launches": K * per_step_launches, "roofline": roofline, "kernels": kernels, "breakdown": breakdown,
+            "gpu_launches": timed_launches, "roofline": roofline, "kernels": kernels, "breakdown": breakdown,
             "whole_step": {"flops": step_flops, "ms": ms / K,
                            "frac": step_flops / (ms / K * 1e-3) / 1e12 / pk["tflops_sustained"]},
             "cpu_baseline": cpu, "train_flops_per_step": step_flops}

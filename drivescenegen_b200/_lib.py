@@ -91,6 +91,7 @@ SIGNATURES = {
     "dsg_version": (C.c_int, []),
     "dsg_last_error": (C.c_char_p, []),
     "dsg_launch_count": (_i64, []),
+    "dsg_count_graph_launches": (None, [_i64]),
     "dsg_device_ok": (C.c_int, []),
     "dsg_ddpm_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),
     "dsg_ddim_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _p]),

@@ -33,6 +33,9 @@ extern "C" {
 int dsg_version(void) { return 100; }
 const char* dsg_last_error(void) { return dsg::g_err; }
 int64_t dsg_launch_count(void) { return dsg::g_launches.load(std::memory_order_relaxed); }
+void dsg_count_graph_launches(int64_t n) {
+  if (n > 0) dsg::g_launches.fetch_add(n, std::memory_order_relaxed);
+}
 int dsg_device_ok(void) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

@@ -18,6 +18,7 @@ Activation gradients are fp16 times a power-of-two factor chosen per step from t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -41,6 +42,13 @@ class TrainProgram(_Program):
         self.dout_ptr = C.c_void_p(0)
         self.slot = 0                 # which of the two flat gradient buffers this program writes (hostapi.training)
         self.on_early_ready = None    # hook(program): the "early" slice of the flat gradient buffer is complete
+        # CUDA graphs of the forward and of the backward (split where the host hook sits): the ~475 launches of a step
+        # leave ~2 ms of gaps between kernels when they are issued one by one.  The first forward + backward of a
+        # program run eagerly (lazy module loading, per-kernel attributes), the second forward captures everything.
+        self.use_graphs = os.environ.get("DSG_TRAIN_GRAPH", "1") != "0"
+        self._eager_fwd = self._eager_bwd = 0
+        self._fwd_graph = None
+        self._bwd_graphs: List[Tuple[Optional[torch.cuda.CUDAGraph], Optional[Callable]]] = []
         super().__init__(eng, batch, h, w)
         self._build_backward()
 
@@ -487,9 +495,83 @@ class TrainProgram(_Program):
         self._bemit("time_embed_bwd", {}, run)
 
     # ------------------------------------------------------------------ execution
+    def _capture(self, dev):
+        """Static input / output buffers + one graph of the forward + one graph per hook-free stretch of the backward."""
+        a, key = self.eng.arena, f"train/{self.b}x{self.h}x{self.w}/graph_io"
+        n_in, n_out = self.b * self.cin * self.h * self.w, self.b * self.cout * self.h * self.w
+        self.g_in = a.get(key + "/in", n_in, torch.float32).view(self.b, self.cin, self.h, self.w)
+        self.g_t = a.get(key + "/t", self.b, torch.float32)
+        self.g_out = a.get(key + "/out", n_out, torch.float32).view(self.b, self.cout, self.h, self.w)
+        self.g_dout = a.get(key + "/dout", n_out, torch.float32).view(self.b, self.cout, self.h, self.w)
+        self.in_ptr = C.c_void_p(self.g_in.data_ptr())
+        self.t_ptr = C.c_void_p(self.g_t.data_ptr())
+        self.out_ptr = C.c_void_p(self.g_out.data_ptr())
+        self.dout_ptr = C.c_void_p(self.g_dout.data_ptr())
+        count = self.lib.dsg_launch_count
+        with torch.cuda.device(dev):
+            g = torch.cuda.CUDAGraph()
+            n0 = count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                st = torch.cuda.current_stream(dev).cuda_stream
+                for op in self.ops:
+                    op(st)
+            self._fwd_graph, self._fwd_launches = g, int(count() - n0)   # reported at every replay
+            pool = g.pool()
+            # the backward: host hooks (the data-parallel boundary) cannot live inside a graph: split there
+            segs, cur = [], []
+            for (name, _), op in zip(self.bwd_info, self.bwd_ops):
+                if name == "early_grads_ready":
+                    segs.append((cur, op))
+                    cur = []
+                else:
+                    cur.append(op)
+            segs.append((cur, None))
+            self._bwd_graphs = []
+            n0 = count()
+            for ops, hook in segs:
+                gb = None
+                if ops:
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb, pool=pool, capture_error_mode="thread_local"):
+                        st = torch.cuda.current_stream(dev).cuda_stream
+                        for op in ops:
+                            op(st)
+                self._bwd_graphs.append((gb, hook))
+            self._bwd_launches = int(count() - n0)
+
+    def run(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not self.use_graphs or self._eager_fwd < 1 or self._eager_bwd < 1:
+            self._eager_fwd += 1
+            self._fwd_graph = None          # an eager run re-points in_ptr / out_ptr: graphs are rebuilt on demand
+            return super().run(sample, t_float, out)
+        if self._fwd_graph is None:
+            self._capture(sample.device)
+        with torch.cuda.device(sample.device):
+            self.g_in.copy_(sample)
+            self.g_t.copy_(t_float)
+            self._fwd_graph.replay()
+            self.lib.dsg_count_graph_launches(self._fwd_launches)
+            if out is None:
+                out = torch.empty_like(self.g_out)
+            out.copy_(self.g_out)
+        return out
+
     def backward(self, dout: torch.Tensor, sample: torch.Tensor):
         """dout: fp32 NCHW gradient of the model output; sample: the forward's fp32 NCHW input (conv_in's wgrad)."""
         assert dout.dtype == torch.float32 and dout.is_contiguous() and dout.is_cuda
+        if self.use_graphs and self._fwd_graph is not None:
+            # the forward that is being differentiated ran from g_in (one forward in flight per shape)
+            with torch.cuda.device(dout.device):
+                self.g_dout.copy_(dout)
+                st = torch.cuda.current_stream(dout.device).cuda_stream
+                for g, hook in self._bwd_graphs:
+                    if g is not None:
+                        g.replay()
+                    if hook is not None:
+                        hook(st)
+                self.lib.dsg_count_graph_launches(self._bwd_launches)
+            return
+        self._eager_bwd += 1
         self.dout_ptr = C.c_void_p(dout.data_ptr())
         self.in_ptr = C.c_void_p(sample.data_ptr())
         with torch.cuda.device(dout.device):
@@ -497,7 +579,21 @@ class TrainProgram(_Program):
             for op in self.bwd_ops:
                 op(st)
 
+    def run_timed(self, sample: torch.Tensor, t_float: torch.Tensor, out: Optional[torch.Tensor] = None):
+        graphs, self.use_graphs = self.use_graphs, False   # per-launch events need the eager path
+        try:
+            return super().run_timed(sample, t_float, out)
+        finally:
+            self.use_graphs = graphs
+
     def backward_timed(self, dout: torch.Tensor, sample: torch.Tensor):
+        graphs, self.use_graphs = self.use_graphs, False
+        try:
+            return self._backward_timed(dout, sample)
+        finally:
+            self.use_graphs = graphs
+
+    def _backward_timed(self, dout: torch.Tensor, sample: torch.Tensor):
         dev = dout.device
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.bwd_ops) + 1)]
         stream = torch.cuda.current_stream(dev)

@@ -37,6 +37,9 @@ int dsg_version(void);
 const char* dsg_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches evidence) */
 int64_t dsg_launch_count(void);
+/* a host that replays a CUDA graph captured from this library's calls reports the graph's kernel count here (the
+ * replay itself does not pass through the library) */
+void dsg_count_graph_launches(int64_t n);
 /* 1 if the current device is sm_100 (tcgen05/TMA kernels can run), 0 otherwise, <0 on error */
 int dsg_device_ok(void);
 

@@ -116,9 +116,11 @@ def test_train_py_then_generation_py_run_unmodified_on_b200(tmp_path, monkeypatc
     assert steps == 20
     # >= 47 tensor-core 3x3 convs in every training forward, issued under train_loop's `model(noisy_pattern, ...)` frame;
     # their data-gradient convs run from `accelerator.backward(loss)` on torch's autograd worker thread (no reference
-    # frame on that Python stack): counted as "other"
-    assert counts["train_loop"] >= steps * 47, counts
-    assert counts["other"] >= steps * 47, counts
+    # frame on that Python stack): counted as "other".  The first step runs launch by launch; the second step's forward
+    # captures the forward AND the backward into CUDA graphs (both under train_loop's frame), and every later step
+    # replays them — those launches are reported through dsg_count_graph_launches (`launched` below), not dsg_conv.
+    assert counts["train_loop"] >= 2 * 47 + 47, counts
+    assert counts["other"] >= 47, counts
     # evaluate(): 750 sampling steps per epoch = replays of a step graph captured (once per epoch's pipeline) from here
     assert counts["evaluate"] >= cfg.num_epochs * 47, counts
     assert launched > steps * 400, launched
