@@ -18,5 +18,7 @@ PARITY STATUS
 * U-Net: PARITY UNPINNED.  ``diffusers`` is not installed here, is not vendored in ``/root/reference`` and
   the reference ships no tests or golden vectors.  The restatement is pinned only by the upstream
   parameter counts (113,673,219 / 56,574,595 / 3,660,803), the state-dict key table and op-level
-  composition from ``torch.nn.functional``.
+  composition from ``torch.nn.functional``.  To pin it: ``python tests/golden/make_unet_golden.py`` where
+  ``diffusers==0.20.0`` is installed writes ``tests/golden/unet_golden.npz`` (eps slices of real diffusers models
+  with deterministic weights); ``tests/test_oracle_unet_golden.py`` then checks this package against it.
 """
