@@ -38,6 +38,7 @@ struct GnBwdArgs {
   float eps; int act;
   float* partial;     // [n][chunks + 1][C][2]: chunk partials (sum g, sum g x), then the per-sample (A_c, B_c)
   int chunks;
+  float* coef;        // [n][C][4] (behind the partials): ga, ybh, pc, qc of dx = ga g + pc x + qc, y / 2 = x ga / 2 + ybh
   const __half* addend;  // optional [n][hw][C]
   __half* dx1; int acc1;
   __half* dx2; int acc2;
@@ -192,6 +193,74 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
   gn_bwd_stats_body<ACT>(a, blockIdx.y, blockIdx.x, a.px_per_block);
 }
 
+// Between the passes: the chunk partials of a sample are summed ONCE (fixed order), per slice of whole groups, into the
+// per-channel coefficients of dx.  Every CTA of the apply pass used to redo this (its own group moments from the
+// integer totals + chunks x C x 2 floats of partials): for the 32 x 32 / 64 x 64 layers (512-1024 channels, few pixels)
+// that prologue moved as many bytes as the pass itself.  grid (slices, n); a slice = as many whole groups as fit 256
+// channels.  Same sums in the same order as before: results are bit-identical to the in-CTA form.
+__global__ void __launch_bounds__(GB_THREADS) gn_bwd_coef_kernel(const GnBwdArgs a, const int groups_per_slice) {
+  const int C = a.c1 + a.c2, cpg = C / a.groups, n = blockIdx.y;
+  const int g0 = blockIdx.x * groups_per_slice;
+  const int ng = min(groups_per_slice, a.groups - g0);
+  const int c0 = g0 * cpg, nc = ng * cpg;
+  __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS], s_m1[GB_MAX_GROUPS], s_m2[GB_MAX_GROUPS];
+  __shared__ float s_gA[GB_THREADS], s_gB[GB_THREADS];
+  pdl_sync();
+  const int tid = threadIdx.x;
+  // group moments from the exact integer totals: identical arithmetic to gn_apply_kernel / gn_moments (one thread per
+  // group walks its channels; integer sums are order-independent)
+  if (tid < ng) {
+    const int g = g0 + tid;
+    long long ts = 0, tq = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const longlong2 tv = *reinterpret_cast<const longlong2*>(
+          c < a.c1 ? a.st1 + ((int64_t)n * a.c1 + c) * 2 : a.st2 + ((int64_t)n * a.c2 + (c - a.c1)) * 2);
+      ts += tv.x; tq += tv.y;
+    }
+    const double mg = (double)ts * a.inv_cnt_s;
+    double vg = (double)tq * a.inv_cnt_q - mg * mg;
+    if (vg < 0.0) vg = 0.0;
+    s_mean[tid] = (float)mg;
+    s_rstd[tid] = rsqrtf((float)vg + a.eps);
+  }
+  float tA = 0.f, tBx = 0.f, gm = 0.f, bt = 0.f;
+  if (tid < nc) {
+    const int c = c0 + tid;
+    const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
+    for (int k = 0; k < a.chunks; ++k) {  // fixed order
+      const float2 t = __ldcg(reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2) + c);
+      tA += t.x; tBx += t.y;
+    }
+    gm = a.gamma[c]; bt = a.beta[c];
+  }
+  __syncthreads();
+  float tB = 0.f;
+  if (tid < nc) {
+    const int c = c0 + tid, gl = tid / cpg;
+    tB = s_rstd[gl] * (tBx - s_mean[gl] * tA);  // sum g * xh
+    float* red = a.partial + ((int64_t)n * (a.chunks + 1) + a.chunks) * C * 2;   // per-sample (A_c, B_c) for the params
+    reinterpret_cast<float2*>(red)[c] = make_float2(tA, tB);
+    s_gA[tid] = gm * tA;
+    s_gB[tid] = gm * tB;
+  }
+  __syncthreads();
+  if (tid < ng) {
+    float m1 = 0.f, m2 = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { m1 += s_gA[c]; m2 += s_gB[c]; }
+    const float inv_cnt = (float)(1.0 / ((double)a.hw * (double)cpg));
+    s_m1[tid] = m1 * inv_cnt;
+    s_m2[tid] = m2 * inv_cnt;
+  }
+  __syncthreads();
+  if (tid < nc) {
+    const int c = c0 + tid, gl = tid / cpg;
+    const float mu = s_mean[gl], rs = s_rstd[gl];
+    const float ga = gm * rs;
+    reinterpret_cast<float4*>(a.coef)[(int64_t)n * C + c] =
+        make_float4(ga, 0.5f * (bt - mu * ga), -rs * rs * s_m2[gl], rs * (mu * rs * s_m2[gl] - s_m1[gl]));
+  }
+}
+
 // Pass 2.  dx = ga * g + pc * x + qc with per-channel pc = -rstd^2 m2, qc = rstd (mean rstd m2 - m1).
 #ifndef GB_APPLY_CTAS
 #define GB_APPLY_CTAS 2
@@ -206,11 +275,9 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_stats_kernel(const GnBwd
 template <int ILP, bool ADD, bool ACC, bool CSUM, bool OSUM>
 __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int n, const int part, const int nparts,
                                                   const int64_t px_per_block) {
-  const int C = a.c1 + a.c2, V = C >> 3, cpg = C / a.groups;
+  const int C = a.c1 + a.c2, V = C >> 3;
   const int ppi = GB_THREADS / V;
-  __shared__ float s_mean[GB_MAX_GROUPS], s_rstd[GB_MAX_GROUPS], s_m1[GB_MAX_GROUPS], s_m2[GB_MAX_GROUPS];
-  __shared__ unsigned long long s_t[GB_MAX_GROUPS][2];
-  __shared__ float s_part[2][GB_THREADS * 8];  // prologue: gamma * A / gamma * B per channel; epilogue: column sums
+  __shared__ float s_part[2][GB_THREADS * 8];  // column sums
   const bool active = (int)threadIdx.x < ppi * V;
   const int v = active ? threadIdx.x % V : 0, prow = active ? threadIdx.x / V : 0;
   const int ch0 = v << 3;
@@ -225,48 +292,18 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
   if (p_end > a.hw) p_end = a.hw;
   int64_t p = p_begin + prow;
   const bool want_osum = OSUM && (from1 ? a.osum1 : a.osum2) != nullptr;
-  gn_moments(a, n, s_mean, s_rstd, s_t);
-  {
-    const float* pp = a.partial + (int64_t)n * (a.chunks + 1) * C * 2;
-    float* red = a.partial + ((int64_t)n * (a.chunks + 1) + a.chunks) * C * 2;  // per-sample (A_c, B_c) for the params
-    for (int c = threadIdx.x; c < C; c += GB_THREADS) {
-      float tA = 0.f, tBx = 0.f;
-      for (int k = 0; k < a.chunks; ++k) {  // fixed order
-        const float2 t = __ldcg(reinterpret_cast<const float2*>(pp + (int64_t)k * C * 2) + c);   // written by other SMs
-        tA += t.x; tBx += t.y;
-      }
-      const int g = c / cpg;
-      const float tB = s_rstd[g] * (tBx - s_mean[g] * tA);  // sum g * xh
-      if (part == 0) reinterpret_cast<float2*>(red)[c] = make_float2(tA, tB);
-      const float gm = a.gamma[c];
-      s_part[0][c] = gm * tA;
-      s_part[1][c] = gm * tB;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < a.groups) {
-      const int g = threadIdx.x;
-      float m1 = 0.f, m2 = 0.f;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { m1 += s_part[0][c]; m2 += s_part[1][c]; }
-      const float inv_cnt = (float)(1.0 / ((double)a.hw * (double)cpg));
-      s_m1[g] = m1 * inv_cnt;
-      s_m2[g] = m2 * inv_cnt;
-    }
-    __syncthreads();
-  }
   float cs_acc[8], os_acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs_acc[j] = 0.f; os_acc[j] = 0.f; }
   if (active) {
     float ga[8], gah[8], ybh[8], pc[8], qc[8];   // y / 2 = x * gah + ybh
+    {
+      const float4* cb = reinterpret_cast<const float4*>(a.coef) + (int64_t)n * C + ch0;   // gn_bwd_coef_kernel
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = ch0 + j, g = ch / cpg;
-      const float mu = s_mean[g], rs = s_rstd[g];
-      ga[j] = a.gamma[ch] * rs;
-      gah[j] = 0.5f * ga[j];
-      ybh[j] = 0.5f * (a.beta[ch] - mu * ga[j]);
-      pc[j] = -rs * rs * s_m2[g];
-      qc[j] = rs * (mu * rs * s_m2[g] - s_m1[g]);
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(cb + j);
+        ga[j] = t.x; gah[j] = 0.5f * t.x; ybh[j] = t.y; pc[j] = t.z; qc[j] = t.w;
+      }
     }
     for (; p < p_end; p += (int64_t)ppi * ILP) {
       uint4 rx[ILP], rd[ILP], ra[ADD ? ILP : 1], ro[ACC ? ILP : 1];
@@ -445,7 +482,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
                     (x2 == nullptr) == (dx2 == nullptr) && c2 % 8 == 0,
                 "dsg_gn_bwd: x2/stats2/dx2/c2 mismatch");
   const int C = c1 + c2;
-  DSG_CHECK_ARG(groups > 0 && groups <= GB_MAX_GROUPS && C % groups == 0 && C <= GB_MAX_C,
+  DSG_CHECK_ARG(groups > 0 && groups <= GB_MAX_GROUPS && C % groups == 0 && C <= GB_MAX_C && C / groups <= GB_THREADS,
                 "dsg_gn_bwd: bad groups %d for C=%d", groups, C);
   DSG_CHECK_ARG(gamma && beta && partial && chunks >= 1 && chunks <= GB_MAX_CHUNKS, "dsg_gn_bwd: bad partial/chunks");
   DSG_CHECK_ARG(n >= 0 && n <= 65535 && hw > 0, "dsg_gn_bwd: bad n/hw");
@@ -453,7 +490,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
                 "dsg_gn_bwd: column sums need an explicit parts > 0");
   DSG_CHECK_ARG(osum2 == nullptr || x2 != nullptr, "dsg_gn_bwd: osum2 without x2");
   DSG_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)dx1 | (uintptr_t)dx2 |
-                  (uintptr_t)addend | (uintptr_t)stats1 | (uintptr_t)stats2) % 16) == 0 && (uintptr_t)partial % 8 == 0,
+                  (uintptr_t)addend | (uintptr_t)stats1 | (uintptr_t)stats2 | (uintptr_t)partial) % 16) == 0,
                 "dsg_gn_bwd: unaligned pointer");
   if (n == 0) return DSG_OK;
   GnBwdArgs a;
@@ -462,6 +499,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   a.x2 = (const __half*)x2; a.c2 = c2; a.st2 = (const long long*)stats2;
   a.gamma = gamma; a.beta = beta; a.eps = eps; a.act = act;
   a.partial = partial; a.chunks = chunks;
+  a.coef = partial + (int64_t)n * (chunks + 1) * C * 2;
   a.addend = (const __half*)addend;
   a.dx1 = (__half*)dx1; a.acc1 = acc1; a.dx2 = (__half*)dx2; a.acc2 = acc2;
   a.colsum = colsum; a.osum1 = osum1; a.osum2 = osum2; a.hw = hw; a.groups = groups;
@@ -470,7 +508,7 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   cudaStream_t st = (cudaStream_t)stream;
   int64_t ctas = parts;
   if (ctas == 0) {
-    ctas = (148 * 4) / n;
+    ctas = (num_sms() * GB_APPLY_CTAS) / n;   // one wave
     if (ctas < 1) ctas = 1;
     const int64_t max_ctas = ceil_div64(hw, 32);
     if (ctas > max_ctas) ctas = max_ctas;
@@ -481,6 +519,14 @@ int dsg_gn_bwd(const void* dy, const void* x1, int32_t c1, const void* stats1, c
   else
     launch_k(gn_bwd_stats_kernel<false>, dim3((unsigned)chunks, n), dim3(GB_THREADS), 0, st, a);
   DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/stats");
+  {
+    const int cpg = C / groups;
+    int gps = GB_THREADS / cpg;   // whole groups per 256-channel slice
+    if (gps < 1) gps = 1;
+    if (gps > groups) gps = groups;
+    launch_k(gn_bwd_coef_kernel, dim3((unsigned)ceil_div(groups, gps), n), dim3(GB_THREADS), 0, st, a, gps);
+    DSG_CUDA_LAUNCH_CHECK("dsg_gn_bwd/coef");
+  }
   a.px_per_block = ceil_div64(hw, ctas);
   launch_k(gn_bwd_apply_pick(addend != nullptr, acc1 != 0 || (acc2 != 0 && c2 > 0), colsum != nullptr,
                              osum1 != nullptr || osum2 != nullptr),

@@ -202,9 +202,10 @@ class TrainProgram(_Program):
         gradient of x1 / x2 — it then also leaves that tensor's column sums (its producer's bias gradient)."""
         eng, lib, b = self.eng, self.lib, self.b
         c, npx = c1 + c2, hw[0] * hw[1]
-        chunks = max(1, min(64, (148 * 4) // b, -(-npx // 64)))
-        partial = self._btmp(self._uniq("gn_partial"), b * (chunks + 1) * c * 2, torch.float32)
-        parts = max(1, min((148 * 4) // b, -(-npx // 32))) if (colsum_to or last1 or last2) else 0
+        wave = int(os.environ.get("DSG_GN_BWD_WAVE", 148 * 2))   # ONE wave of the 2-CTA-per-SM kernels (measured: 2 waves 6-18 % slower)
+        chunks = max(1, min(64, wave // b, -(-npx // 64)))
+        partial = self._btmp(self._uniq("gn_partial"), b * (chunks + 1) * c * 2 + b * c * 4, torch.float32)
+        parts = max(1, min(wave // b, -(-npx // 32))) if (colsum_to or last1 or last2) else 0
         colsum = self._btmp(self._uniq("gn_colsum"), max(1, b * parts * c), torch.float32) if colsum_to else None
         if self._sizing:
             return

@@ -6,6 +6,7 @@ Every function requires CUDA tensors and raises ``DsgError`` on failure — no f
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -300,13 +301,15 @@ def gn_bwd(dy, x1, x2, gamma, beta, groups: int, eps: float, act: int, stats1=No
         stats1 = gn_stats(x1)
     if x2 is not None and stats2 is None:
         stats2 = gn_stats(x2)
-    chunks = max(1, min(64, (148 * 4) // n, -(-hw // 64)))
-    partial = torch.empty((n, chunks + 1, c, 2), dtype=torch.float32, device=dy.device)
+    wave = int(os.environ.get("DSG_GN_BWD_WAVE", 148 * 2))   # ONE wave of the 2-CTA-per-SM kernels (measured: 2 waves 6-18 % slower)
+    chunks = max(1, min(64, wave // n, -(-hw // 64)))
+    # chunk partials + the per-sample (sum g, sum g xh) slot, then the per-channel dx coefficients [n][c][4]
+    partial = torch.empty(n * (chunks + 1) * c * 2 + n * c * 4, dtype=torch.float32, device=dy.device)
     if dx1 is None:
         dx1 = torch.empty_like(x1)
     if x2 is not None and dx2 is None:
         dx2 = torch.empty_like(x2)
-    parts = max(1, min((148 * 4) // n, -(-hw // 32))) if (want_colsum or want_osum) else 0
+    parts = max(1, min(wave // n, -(-hw // 32))) if (want_colsum or want_osum) else 0
     colsum = torch.empty((n, parts, c), dtype=torch.float32, device=dy.device) if want_colsum else None
     osum1 = torch.empty((n, parts, c1), dtype=torch.float32, device=dy.device) if want_osum else None
     osum2 = torch.empty((n, parts, c2), dtype=torch.float32, device=dy.device) if (want_osum and c2) else None

@@ -272,9 +272,10 @@ int dsg_lin_wgrad_small(const float* dy, int32_t ldy, int32_t dy_off, const floa
                         void* stream);
 
 /* GroupNorm(+SiLU) backward over cat(x1, x2) (see dsg_gn_apply for the forward and the statistics format).
- *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: float[n][chunks + 1][c1+c2][2] scratch
- *   (chunk partials, then one slot per sample holding the sums behind d beta / d gamma, read by dsg_gn_bwd_params),
- *   1 <= chunks <= 64.
+ *   dy: h16 [n][hw][c1+c2] gradient w.r.t. the forward OUTPUT.  partial: scratch of
+ *   n * (chunks + 1) * (c1+c2) * 2 + n * (c1+c2) * 4 floats: [n][chunks + 1][c1+c2][2] (chunk partials, then one slot per
+ *   sample holding the sums behind d beta / d gamma, read by dsg_gn_bwd_params) followed by the per-channel coefficients
+ *   of dx [n][c1+c2][4] that a small kernel between the two passes derives from them; 1 <= chunks <= 64.
  *   addend (may be NULL): h16 [n][hw][c1+c2] added to the input gradient (the ResnetBlock shortcut's gradient).
  *   dx1 / dx2: h16 gradients of x1 / x2; accN != 0 adds to the existing content (tensor with two consumers).
  *   parts: CTAs per sample of the apply pass (0 = automatic, only without column sums).  Optional per-CTA column sums
