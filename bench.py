@@ -319,7 +319,9 @@ def train_record(args, dev, rank, world, K, W, with_cpu_baseline):
                    "achieved_gbs_algorithmic": gnb_alg / (gnb_ms * 1e-3) / 1e9,
                    "frac": gnb_alg / (gnb_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                    "achieved_gbs_executed": gnb_bytes / (gnb_ms * 1e-3) / 1e9,
-                   "frac_executed": gnb_bytes / (gnb_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                   "frac_executed": gnb_bytes / (gnb_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                   "note": "reported against HBM; ncu shows the two kernels instruction-issue-bound (52-61 % issue-active "
+                           "at 23 % occupancy, profiles/r2o_ncu_full_gn_bwd_streamed_vs_register.txt)"},
         "attention_bwd": {"bound": "mufu", "ms": agg(bwd, "attention_bwd")[0]},
     }
     breakdown = {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_conv_ms": cv_ms, "wgrad_ms": wg_ms, "dgrad_ms": dg_ms,
