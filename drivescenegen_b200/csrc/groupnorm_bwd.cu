@@ -101,7 +101,10 @@ __device__ __forceinline__ __half2 silu_grad_h2(__half2 h) {
 
 // Pass 1.  Per (sample, pixel chunk, channel): sum g and sum g * x (raw x: the centring is applied when the chunks are
 // combined, sum g * xh = rstd * (sum g x - mean * sum g), which keeps the per-thread state small).
-constexpr int GB_ILP = 4;
+#ifndef GB_ILP_DEF
+#define GB_ILP_DEF 6   /* 4 -> 6: 1-2.5 % (same-box sweep, one-wave grids) */
+#endif
+constexpr int GB_ILP = GB_ILP_DEF;
 template <bool ACT>
 __device__ __forceinline__ void gn_bwd_stats_body(const GnBwdArgs& a, const int n, const int chunk,
                                                   const int64_t px_per_block) {
@@ -392,7 +395,10 @@ __device__ __forceinline__ void gn_bwd_apply_body(const GnBwdArgs& a, const int 
 template <bool ADD, bool ACC, bool CSUM, bool OSUM>
 __global__ void __launch_bounds__(GB_THREADS, GB_APPLY_CTAS) gn_bwd_apply_kernel(const GnBwdArgs a) {
   pdl_sync();
-  gn_bwd_apply_body<GB_APPLY_ILP, ADD, ACC, CSUM, OSUM>(a, blockIdx.y, blockIdx.x, gridDim.x, a.px_per_block);
+  // four pixels in flight per thread where the registers allow it (1-3 %); with an addend AND a previous content that is
+  // 4 x 4 uint4 of loads and spills at two CTAs per SM: three there
+  gn_bwd_apply_body<(ADD && ACC) ? GB_APPLY_ILP : GB_APPLY_ILP + 1, ADD, ACC, CSUM, OSUM>(a, blockIdx.y, blockIdx.x,
+                                                                                          gridDim.x, a.px_per_block);
 }
 typedef void (*GnBwdApplyFn)(const GnBwdArgs);
 template <int I>

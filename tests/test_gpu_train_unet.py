@@ -156,6 +156,36 @@ def _train_loop(model, accelerator, optimizer, lr_sched, sched, batches, fused_e
     return losses
 
 
+def test_training_graphs_are_bit_identical_to_launch_by_launch(monkeypatch):
+    """From its second step on a training program replays its forward and backward as CUDA graphs (same kernels, same
+    order, static buffers): parameters and losses after 6 steps are bit-identical to the launch-by-launch path, the graphs
+    really are in use, and their replays are reported to the library's launch counter."""
+    from drivescenegen_b200 import _lib
+    from drivescenegen_b200.hostapi import Accelerator, DDPMScheduler, get_cosine_schedule_with_warmup
+    g = torch.Generator().manual_seed(22)
+    batches = [torch.rand(4, 3, 64, 64, generator=g).mul(2).sub(1).to(_dev()) for _ in range(6)]
+    results = []
+    for graphs in ("1", "0"):
+        monkeypatch.setenv("DSG_TRAIN_GRAPH", graphs)   # read when a TrainProgram is built
+        _, model = _pair(CFG_REF, seed=4)
+        model.train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+        lr_sched = get_cosine_schedule_with_warmup(optimizer=opt, num_warmup_steps=2, num_training_steps=8)
+        acc = Accelerator(mixed_precision="fp16", gradient_accumulation_steps=1)
+        n0 = _lib.launch_count()
+        losses = _train_loop(model, acc, opt, lr_sched, DDPMScheduler(), batches, True)
+        launches = _lib.launch_count() - n0
+        progs = list(model.engine(train=True).train_programs.values())
+        captured = [p for p in progs if p._fwd_graph is not None]
+        assert bool(captured) == (graphs == "1")
+        results.append((losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone(), launches))
+    (l_g, p_g, n_g), (l_e, p_e, n_e) = results
+    assert l_g == l_e, (l_g, l_e)
+    assert torch.equal(p_g, p_e)
+    # the graph run executes the same kernels + one extra pass through the capture (which launches nothing)
+    assert n_g >= n_e, (n_g, n_e)
+
+
 @pytest.mark.parametrize("precision", ["fp16", "no"])
 def test_reference_train_loop_sequence_fused_vs_torch_optimizer(precision):
     """The reference's training-loop call sequence through the shims: the fused flat-buffer clip + AdamW path (what
