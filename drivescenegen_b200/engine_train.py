@@ -546,7 +546,13 @@ class TrainProgram(_Program):
             self._fwd_graph = None          # an eager run re-points in_ptr / out_ptr: graphs are rebuilt on demand
             return super().run(sample, t_float, out)
         if self._fwd_graph is None:
-            self._capture(sample.device)
+            try:
+                self._capture(sample.device)
+            except Exception as e:   # noqa: BLE001 — e.g. a capture-unsafe call on this stream: keep training, launch by launch
+                import warnings
+                warnings.warn(f"dsg_b200: CUDA-graph capture of the training step failed ({e}); running launch by launch")
+                self.use_graphs, self._fwd_graph, self._bwd_graphs = False, None, []
+                return super().run(sample, t_float, out)
         with torch.cuda.device(sample.device):
             self.g_in.copy_(sample)
             self.g_t.copy_(t_float)
