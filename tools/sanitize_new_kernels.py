@@ -53,6 +53,33 @@ for (mode, cin, cout, hw) in [(0, 64, 64, 16), (0, 128, 256, 16), (3, 64, 128, 1
     dy = torch.randn(2, ohw, ohw, cout, generator=g).half().to(d)
     ops.conv_wgrad(mode, x, dy)
 
+# round 2: GroupNorm backward (statistics / per-sample coefficients / operand-flag-specialised apply variants), the TMA-store
+# conv epilogue (64 -> 64 and 1x1 convs), the shared-memory staged weight re-pack, the bilinear resize
+for (n, hh, ww, c1, c2, act, add, acc) in [(2, 16, 16, 64, 0, 1, False, False), (2, 24, 8, 128, 64, 1, True, True),
+                                           (1, 8, 8, 512, 512, 1, False, True), (2, 16, 16, 256, 0, 0, True, False)]:
+    c = c1 + c2
+    x1 = torch.randn(n, hh, ww, c1, generator=g).half().to(d)
+    x2 = torch.randn(n, hh, ww, c2, generator=g).half().to(d) if c2 else None
+    dyh = torch.randn(n, hh, ww, c, generator=g).half().to(d)
+    addend = torch.randn(n, hh, ww, c, generator=g).half().to(d) if add else None
+    ops.gn_bwd(dyh, x1, x2, torch.ones(c, device=d), torch.zeros(c, device=d), 32, 1e-5, act, addend=addend,
+               dx1=torch.zeros_like(x1) if acc else None, dx2=torch.zeros_like(x2) if (acc and c2) else None,
+               acc1=acc, acc2=acc and c2 > 0, want_colsum=True, want_osum=True)
+for (mode, cin, cout) in [(0, 64, 64), (3, 64, 128), (3, 128, 64)]:
+    xh = torch.randn(2, 32, 32, cin, generator=g).half().to(d)
+    kk = 1 if mode == 3 else 3
+    ops.conv(mode, xh, ops.pack_conv_weight(mode, (torch.randn(cout, cin, kk, kk, generator=g) * 0.05).to(d)), cout,
+             bias=torch.zeros(cout, device=d))
+jobs = []
+for cout, cin in ((64, 64), (72, 40), (136, 200)):
+    w3 = torch.randn(cout, cin, 3, 3, generator=g).to(d)
+    jobs += [(m, w3, None) for m in (0, 1, 2, 10, 11, 12)]
+    jobs += [(0, w3, torch.randn(cout, 48, generator=g).to(d))]
+    w1 = torch.randn(cout, cin, 1, 1, generator=g).to(d)
+    jobs += [(3, w1, None), (13, w1, None)]
+ops.pack_conv_weights_batched(jobs)
+raster.image_to_sample(rng.integers(0, 256, (2, 50, 70, 3), dtype=np.uint8), channels=3, size=(32, 48))
+
 dy = torch.randn(4, 600, generator=g).to(d)
 wl = torch.randn(600, 256, generator=g).to(d)
 ops.lin_dgrad_small(dy, wl)
