@@ -32,6 +32,17 @@ def test_cabi_exports_every_declared_symbol(built_lib):
     assert l.dsg_version() == 100
     assert l.dsg_packed_k(0, 64, 128) == 9 * 64 + 128 and l.dsg_packed_k(2, 64, 0) == 256
     assert l.dsg_packed_rows(2, 64) == 256
+    # host-side planning of the batched weight re-pack: one block per output channel for the forward layouts, one per
+    # 128 co x 8 ci (64 ci for 1x1) tile for the data-gradient layouts, -1 when a source row does not fit the staging
+    assert l.dsg_pack_job_blocks(0, 512, 1024, 1024) == 512
+    assert l.dsg_pack_job_blocks(2, 128, 128, 0) == 128
+    assert l.dsg_pack_job_blocks(10, 200, 72, 0) == 9 * 2 and l.dsg_pack_job_blocks(13, 512, 512, 0) == 8 * 4
+    assert l.dsg_pack_job_blocks(0, 64, 2048, 0) == -1 and l.dsg_pack_job_blocks(5, 64, 64, 0) == -1
+    # replays of a captured graph are reported by the host: the counter is the number of kernels executed
+    n0 = l.dsg_launch_count()
+    l.dsg_count_graph_launches(475)
+    l.dsg_count_graph_launches(-3)
+    assert l.dsg_launch_count() - n0 == 475
 
 
 def test_conv_args_struct_layout_matches_header(tmp_path, built_lib):
